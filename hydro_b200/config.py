@@ -1,0 +1,244 @@
+"""Parameter handling for the GPU path: the reference's parameter names are the API.
+
+`Params` accepts the same keys as the reference's per-experiment stores
+P_int / P_double / P_bool / P_string / P_vect (control/experiment.hpp:50-54) and the
+same `set <type> <name> <value>` lines as a .hydroconf script
+(control/console.cpp:276-314).  Defaults are those of examples/general.hydroconf.
+`Params.to_struct()` produces the `hg_config` of include/hydro_gpu.h.
+"""
+import ctypes as C
+import re
+
+HG_MAX_PHASES = 3
+LINEAR_SOLVERS = {"lu": 0, "lu_relaxed": 1, "gauss_seidel": 2, "jacobi": 3}
+BC_KINDS = {"wall": 0, "inlet": 1, "outlet": 2}
+SIDES = ["left", "right", "bottom", "top", "close", "far"]
+
+d3 = C.c_double * 3
+dP = C.c_double * HG_MAX_PHASES
+
+
+class HgConfig(C.Structure):
+    """ctypes mirror of `struct hg_config` (include/hydro_gpu.h); keep in sync."""
+    _fields_ = [
+        ("dim", C.c_int), ("Nx", C.c_int), ("Ny", C.c_int), ("Nz", C.c_int),
+        ("A", d3), ("B", d3), ("box_A", d3), ("box_B", d3),
+        ("condition_kind", C.c_int * 6), ("condition_velocity", d3 * 6),
+        ("pressure_fixed_enable", C.c_int), ("pressure_fixed_point", d3),
+        ("pressure_fixed_value", C.c_double),
+        ("initial_velocity", d3), ("initial_pois", C.c_int), ("initial_sin_enable", C.c_int),
+        ("initial_sin_n", d3), ("initial_sin_lambda", C.c_double), ("initial_sin_phase", C.c_double),
+        ("A1", d3), ("B1", d3), ("A2", d3), ("B2", d3),
+        ("IC", d3), ("IR", C.c_double), ("IC2", d3), ("IR2", C.c_double),
+        ("initial_volume_fraction", dP), ("initial_volume_fraction_smooth_times", C.c_int),
+        ("dt", C.c_double), ("dt_auto", C.c_int), ("cfl", C.c_double), ("cfl_advection", C.c_double),
+        ("num_phases", C.c_int), ("density", dP), ("viscosity", dP), ("conductivity", dP),
+        ("gravity", d3), ("force", d3), ("sigma", C.c_double),
+        ("fluid_enable", C.c_int), ("advection_enable", C.c_int),
+        ("convergence_tolerance", C.c_double), ("num_iterations_limit", C.c_int),
+        ("velocity_relaxation_factor", C.c_double), ("pressure_relaxation_factor", C.c_double),
+        ("rhie_chow_factor", C.c_double),
+        ("time_second_order", C.c_int), ("simpler", C.c_int), ("force_geometric_average", C.c_int),
+        ("guess_extrapolation", C.c_double), ("meshvel", d3),
+        ("linear_solver_velocity", C.c_int), ("linear_solver_pressure", C.c_int),
+        ("linear_solver_heat", C.c_int),
+        ("lu_relaxed_tolerance", C.c_double), ("lu_relaxed_num_iters_limit", C.c_int),
+        ("lu_relaxed_relaxation_factor", C.c_double),
+        ("density_smooth_times", C.c_int), ("viscosity_smooth_times", C.c_int),
+        ("force_smooth_times", C.c_int),
+        ("advection_dt_factor", C.c_double), ("tvd_split", C.c_int), ("sharp", C.c_double),
+        ("heat_enable", C.c_int), ("temperature_initial", C.c_double),
+        ("heat_box_lb", d3), ("heat_box_rt", d3), ("heat_box_temperature", C.c_double),
+        ("heat_relaxation_factor", C.c_double), ("time_second_order_heat", C.c_int),
+        ("world_size", C.c_int), ("rank", C.c_int), ("device", C.c_int),
+        ("nccl_unique_id", C.c_void_p),
+        ("pressure_sweeps_per_check", C.c_int), ("reserved", C.c_int * 7),
+    ]
+
+
+class HgStepStats(C.Structure):
+    """ctypes mirror of `struct hg_step_stats`."""
+    _fields_ = [
+        ("simple_iterations", C.c_int), ("convergence_indicator", C.c_double),
+        ("pressure_sweeps_total", C.c_int), ("advection_substeps", C.c_int),
+        ("dt", C.c_double), ("time", C.c_double), ("pressure_last_diff", C.c_double),
+        ("volume", dP), ("mass", dP), ("pd_min", dP), ("pd_max", dP),
+        ("center", d3 * HG_MAX_PHASES), ("velocity", d3 * HG_MAX_PHASES),
+    ]
+
+
+# field ids (enum hg_field)
+F = dict(
+    VELOCITY_X=0, VELOCITY_Y=1, VELOCITY_Z=2, PRESSURE=3, VOLUME_FLUX=4,
+    PARTIAL_DENSITY_0=5, PARTIAL_DENSITY_1=6, PARTIAL_DENSITY_2=7, TEMPERATURE=8,
+    DENSITY=9, VISCOSITY=10, FORCE_X=11, FORCE_Y=12, FORCE_Z=13,
+    VOLUME_FRACTION_0=14, VOLUME_FRACTION_1=15, VOLUME_FRACTION_2=16,
+    STFORCE_X=17, STFORCE_Y=18, STFORCE_Z=19,
+    VELOCITY_PREV_X=20, VELOCITY_PREV_Y=21, VELOCITY_PREV_Z=22, PRESSURE_PREV=23,
+    VOLUME_FLUX_PREV=24, EXCLUDED=25, CONDUCTIVITY=26,
+)
+FACE_FIELDS = {F["VOLUME_FLUX"], F["VOLUME_FLUX_PREV"]}
+
+# examples/general.hydroconf (only the keys the hot path reads)
+GENERAL_DEFAULTS = {
+    "MODULE": "hydro2D_uniform_MPI",
+    "A": (0, 0, 0), "B": (1, 1, 1), "A1": (0, 0, 0), "B1": (0, 0, 1), "A2": (0, 0, 0), "B2": (0, 0, 1),
+    "box_A": (0, 0), "box_B": (0, 0), "IC": (0., 0., 0.), "IR": 0., "IC2": (0., 0., 0.), "IR2": 0.,
+    "Nx": 100, "Ny": 100, "Nz": 5, "T": 1., "dt": 0.01, "dt_auto": 0, "cfl": 0.5, "cfl_advection": 0.5,
+    "num_phases": 1, "gravity": (0., 0, 0), "force": (0., 0., 0.), "sigma": 0.,
+    "density_0": 1., "density_1": 1., "density_2": 1., "viscosity_0": 1., "viscosity_1": 1., "viscosity_2": 1.,
+    "deforming_velocity": 0, "initial_velocity": (0, 0),
+    "condition_top": "wall 0 0 0", "condition_bottom": "wall 0 0 0", "condition_left": "wall 0 0 0",
+    "condition_right": "wall 0 0 0", "condition_close": "wall 0 0 0", "condition_far": "wall 0 0 0",
+    "chemistry": "steady", "chem_intensity": 0., "radiation_enable": 0,
+    "heat_enable": 0, "linear_solver_heat": "lu", "heat_box_lb": (0, 0, 0), "heat_box_rt": (0, 0, 0),
+    "conductivity_0": 1., "conductivity_1": 1., "conductivity_2": 1., "temperature_initial": 0.,
+    "heat_box_temperature": 0., "heat_relaxation_factor": 1., "time_second_order_heat": 1,
+    "fluid_enable": 1, "advection_enable": 1, "advection_solver": "tvd", "advection_dt_factor": 0.1,
+    "tvd_split": 0, "convergence_tolerance": 1e-2, "num_iterations_limit": 10,
+    "velocity_relaxation_factor": 0.8, "pressure_relaxation_factor": 0.9,
+    "linear_solver_velocity": "lu", "linear_solver_pressure": "gauss_seidel",
+    "lu_relaxed_relaxation_factor": 1.9, "lu_relaxed_num_iters_limit": 1000, "lu_relaxed_tolerance": 1e-3,
+    "time_second_order": 1, "rhie_chow_factor": 1., "simpler": 0,
+    "initial_volume_fraction_smooth_times": 2, "density_smooth_times": 2, "viscosity_smooth_times": 2,
+    "force_smooth_times": 0, "force_geometric_average": 0, "guess_extrapolation": 0.,
+    "compressible_enable": 0, "meshvel": (0, 0, 0), "sharp": 0.,
+}
+
+MODULE_DIM = {"hydro2D_uniform_MPI": 2, "hydro2d": 2, "hydro3D_uniform_MPI": 3, "hydro3d": 3,
+              # aliases registered by the GPU module
+              "hydro2d_gpu": 2, "hydro3d_gpu": 3}
+
+
+def _vec3(v):
+    v = list(v) + [0.0] * 3
+    return [float(x) for x in v[:3]]
+
+
+class Params(dict):
+    """Key-value parameters with the reference's names; missing keys raise like P_x["k"]
+    (common/data_structures.hpp:238-242)."""
+
+    def __init__(self, *overrides, **kw):
+        super().__init__(GENERAL_DEFAULTS)
+        for o in overrides:
+            self.update(o)
+        self.update(kw)
+
+    # -- .hydroconf text -----------------------------------------------------
+    _set_re = re.compile(r"^\s*set\s+(\w+)\s+(\w+)\s+(.*?)\s*$")
+
+    def read_hydroconf(self, text):
+        """Apply `set <type> <name> <value>` / `del <name>` lines (console.cpp:276-314)."""
+        for raw in text.splitlines():
+            line = raw.split("#", 1)[0].strip()
+            if not line:
+                continue
+            if line.startswith("del "):
+                self.pop(line.split()[1], None)
+                continue
+            m = self._set_re.match(line)
+            if not m:
+                continue  # console commands (ae, run, init, start ...) are the caller's business
+            typ, name, val = m.groups()
+            val = re.sub(r"\$\((\w+)\)|\$(\w+)", lambda g: str(self[g.group(1) or g.group(2)]), val)
+            if typ in ("int", "c_int"):
+                self[name] = int(val)
+            elif typ in ("double", "c_double"):
+                self[name] = float(val)
+            elif typ in ("bool", "c_bool"):
+                self[name] = int(val)
+            elif typ == "vect":
+                self[name] = tuple(float(x) for x in val.strip("() ").replace(",", " ").split())
+            else:
+                self[name] = val.strip('"')
+        return self
+
+    # -- struct -----------------------------------------------------------------
+    def to_struct(self, world_size=1, rank=0, device=0, nccl_unique_id=None):
+        p = self
+
+        def need(k):
+            if k not in p:
+                raise KeyError("'%s' undefined" % k)
+            return p[k]
+
+        c = HgConfig()
+        module = need("MODULE")
+        if module not in MODULE_DIM:
+            raise ValueError("Unknown module '%s'" % module)
+        c.dim = MODULE_DIM[module]
+        c.Nx, c.Ny, c.Nz = int(need("Nx")), int(need("Ny")), int(need("Nz")) if c.dim == 3 else 1
+        for name in ("A", "B", "box_A", "box_B", "A1", "B1", "A2", "B2", "IC", "IC2", "gravity", "force",
+                     "meshvel", "heat_box_lb", "heat_box_rt"):
+            setattr(c, name, d3(*_vec3(need(name))))
+        c.IR, c.IR2 = float(need("IR")), float(need("IR2"))
+        for i, side in enumerate(SIDES):
+            words = str(need("condition_" + side)).split()
+            if words[0] not in BC_KINDS:
+                raise ValueError("Parse: Unknown boundary condition type")
+            c.condition_kind[i] = BC_KINDS[words[0]]
+            vel = [float(w) for w in words[1:1 + c.dim]]
+            c.condition_velocity[i] = d3(*_vec3(vel))
+        if "pressure_fixed_point" in p:
+            c.pressure_fixed_enable = 1
+            c.pressure_fixed_point = d3(*_vec3(p["pressure_fixed_point"]))
+            c.pressure_fixed_value = float(p.get("pressure_fixed_value", 0.0))
+        c.initial_velocity = d3(*_vec3(p.get("initial_velocity", (0, 0, 0))))
+        c.initial_pois = int(bool(p.get("initial_pois", 0)))
+        if "initial_sin_n" in p:
+            c.initial_sin_enable = 1
+            c.initial_sin_n = d3(*_vec3(p["initial_sin_n"]))
+            c.initial_sin_lambda = float(need("initial_sin_lambda"))
+            c.initial_sin_phase = float(need("initial_sin_phase"))
+        c.num_phases = int(need("num_phases"))
+        for i in range(min(c.num_phases, HG_MAX_PHASES)):
+            c.density[i] = float(need("density_%d" % i))
+            c.viscosity[i] = float(need("viscosity_%d" % i))
+            c.conductivity[i] = float(need("conductivity_%d" % i))
+            c.initial_volume_fraction[i] = float(p.get("initial_volume_fraction_%d" % i, 0.0))
+        for name in ("initial_volume_fraction_smooth_times", "dt_auto", "fluid_enable", "advection_enable",
+                     "num_iterations_limit", "time_second_order", "simpler", "force_geometric_average",
+                     "lu_relaxed_num_iters_limit", "density_smooth_times", "viscosity_smooth_times",
+                     "force_smooth_times", "tvd_split", "heat_enable", "time_second_order_heat"):
+            setattr(c, name, int(need(name)))
+        for name in ("dt", "cfl", "cfl_advection", "sigma", "convergence_tolerance", "velocity_relaxation_factor",
+                     "pressure_relaxation_factor", "rhie_chow_factor", "guess_extrapolation",
+                     "lu_relaxed_tolerance", "lu_relaxed_relaxation_factor", "advection_dt_factor", "sharp",
+                     "temperature_initial", "heat_box_temperature", "heat_relaxation_factor"):
+            setattr(c, name, float(need(name)))
+        for name in ("linear_solver_velocity", "linear_solver_pressure", "linear_solver_heat"):
+            v = need(name)
+            if v not in LINEAR_SOLVERS:
+                raise ValueError("Unknown linear solver '%s'" % v)
+            setattr(c, name, LINEAR_SOLVERS[v])
+        if need("advection_solver") != "tvd":
+            raise ValueError("only advection_solver tvd is on the GPU path")
+        c.world_size, c.rank, c.device = world_size, rank, device
+        if nccl_unique_id is not None:
+            self._uid_buf = C.create_string_buffer(bytes(nccl_unique_id), 128)
+            c.nccl_unique_id = C.cast(self._uid_buf, C.c_void_p)
+        c.pressure_sweeps_per_check = int(p.get("pressure_sweeps_per_check", 0))
+        return c
+
+    def hydroconf_lines(self):
+        """The same parameters as `set` lines for the reference binary."""
+        out = []
+        for k, v in self.items():
+            if k == "pressure_sweeps_per_check":
+                continue
+            if isinstance(v, str):
+                out.append('set string %s "%s"' % (k, v) if " " in v else "set string %s %s" % (k, v))
+            elif isinstance(v, (tuple, list)):
+                out.append("set vect %s (%s)" % (k, ", ".join(repr(float(x)) for x in v)))
+            elif isinstance(v, float):
+                out.append("set double %s %r" % (k, v))
+            else:
+                typ = "bool" if k in _BOOL_KEYS else "int"
+                out.append("set %s %s %d" % (typ, k, int(v)))
+        return out
+
+
+_BOOL_KEYS = {"dt_auto", "deforming_velocity", "radiation_enable", "heat_enable", "time_second_order_heat",
+              "fluid_enable", "advection_enable", "tvd_split", "time_second_order", "simpler",
+              "force_geometric_average", "compressible_enable", "initial_pois", "no_output", "no_mesh_output"}
