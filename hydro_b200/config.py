@@ -39,7 +39,7 @@ class HgConfig(C.Structure):
         ("velocity_relaxation_factor", C.c_double), ("pressure_relaxation_factor", C.c_double),
         ("rhie_chow_factor", C.c_double),
         ("time_second_order", C.c_int), ("simpler", C.c_int), ("force_geometric_average", C.c_int),
-        ("guess_extrapolation", C.c_double), ("meshvel", d3),
+        ("guess_extrapolation", C.c_double), ("meshvel", d3), ("meshvel_output", C.c_int),
         ("linear_solver_velocity", C.c_int), ("linear_solver_pressure", C.c_int),
         ("linear_solver_heat", C.c_int),
         ("lu_relaxed_tolerance", C.c_double), ("lu_relaxed_num_iters_limit", C.c_int),
@@ -79,30 +79,317 @@ F = dict(
 )
 FACE_FIELDS = {F["VOLUME_FLUX"], F["VOLUME_FLUX_PREV"]}
 
-# examples/general.hydroconf (only the keys the hot path reads)
+# examples/general.hydroconf: every key with its store type (the reference's module ctor
+# throws "'k' undefined" for any missing one, common/data_structures.hpp:238-242)
 GENERAL_DEFAULTS = {
-    "MODULE": "hydro2D_uniform_MPI",
-    "A": (0, 0, 0), "B": (1, 1, 1), "A1": (0, 0, 0), "B1": (0, 0, 1), "A2": (0, 0, 0), "B2": (0, 0, 1),
-    "box_A": (0, 0), "box_B": (0, 0), "IC": (0., 0., 0.), "IR": 0., "IC2": (0., 0., 0.), "IR2": 0.,
-    "Nx": 100, "Ny": 100, "Nz": 5, "T": 1., "dt": 0.01, "dt_auto": 0, "cfl": 0.5, "cfl_advection": 0.5,
-    "num_phases": 1, "gravity": (0., 0, 0), "force": (0., 0., 0.), "sigma": 0.,
-    "density_0": 1., "density_1": 1., "density_2": 1., "viscosity_0": 1., "viscosity_1": 1., "viscosity_2": 1.,
-    "deforming_velocity": 0, "initial_velocity": (0, 0),
-    "condition_top": "wall 0 0 0", "condition_bottom": "wall 0 0 0", "condition_left": "wall 0 0 0",
-    "condition_right": "wall 0 0 0", "condition_close": "wall 0 0 0", "condition_far": "wall 0 0 0",
-    "chemistry": "steady", "chem_intensity": 0., "radiation_enable": 0,
-    "heat_enable": 0, "linear_solver_heat": "lu", "heat_box_lb": (0, 0, 0), "heat_box_rt": (0, 0, 0),
-    "conductivity_0": 1., "conductivity_1": 1., "conductivity_2": 1., "temperature_initial": 0.,
-    "heat_box_temperature": 0., "heat_relaxation_factor": 1., "time_second_order_heat": 1,
-    "fluid_enable": 1, "advection_enable": 1, "advection_solver": "tvd", "advection_dt_factor": 0.1,
-    "tvd_split": 0, "convergence_tolerance": 1e-2, "num_iterations_limit": 10,
-    "velocity_relaxation_factor": 0.8, "pressure_relaxation_factor": 0.9,
-    "linear_solver_velocity": "lu", "linear_solver_pressure": "gauss_seidel",
-    "lu_relaxed_relaxation_factor": 1.9, "lu_relaxed_num_iters_limit": 1000, "lu_relaxed_tolerance": 1e-3,
-    "time_second_order": 1, "rhie_chow_factor": 1., "simpler": 0,
-    "initial_volume_fraction_smooth_times": 2, "density_smooth_times": 2, "viscosity_smooth_times": 2,
-    "force_smooth_times": 0, "force_geometric_average": 0, "guess_extrapolation": 0.,
-    "compressible_enable": 0, "meshvel": (0, 0, 0), "sharp": 0.,
+    'MODULE': 'hydro2D_uniform_MPI',
+    'plt_title': 'Template',
+    'A': (0.0, 0.0, 0.0),
+    'B': (1.0, 1.0, 1.0),
+    'A1': (0.0, 0.0, 0.0),
+    'B1': (0.0, 0.0, 1.0),
+    'A2': (0.0, 0.0, 0.0),
+    'B2': (0.0, 0.0, 1.0),
+    'box_A': (0.0, 0.0),
+    'box_B': (0.0, 0.0),
+    'IC': (0.0, 0.0, 0.0),
+    'IR': 0.0,
+    'IC2': (0.0, 0.0, 0.0),
+    'IR2': 0.0,
+    'Nx': 100,
+    'Ny': 100,
+    'Nz': 5,
+    'T': 1.0,
+    'dt': 0.01,
+    'dt_auto': 0,
+    'cfl': 0.5,
+    'cfl_advection': 0.5,
+    'num_phases': 1,
+    'gravity': (0.0, 0.0, 0.0),
+    'force': (0.0, 0.0, 0.0),
+    'sigma': 0.0,
+    'density_0': 1.0,
+    'density_1': 1.0,
+    'density_2': 1.0,
+    'viscosity_0': 1.0,
+    'viscosity_1': 1.0,
+    'viscosity_2': 1.0,
+    'molar_0': 1.0,
+    'molar_1': 1.0,
+    'molar_2': 1.0,
+    'deforming_velocity': 0,
+    'initial_velocity': (0.0, 0.0),
+    'condition_top': 'wall 0 0 0',
+    'condition_bottom': 'wall 0 0 0',
+    'condition_left': 'wall 0 0 0',
+    'condition_right': 'wall 0 0 0',
+    'condition_close': 'wall 0 0 0',
+    'condition_far': 'wall 0 0 0',
+    'chemistry': 'steady',
+    'chem_intensity': 0.0,
+    'reaction_zone_lb': (0.0, 0.0, 0.0),
+    'reaction_zone_rt': (0.0, 0.0, 0.0),
+    'radiation_enable': 0,
+    'radiation_intensity': 1.0,
+    'radiation_direction': (0.0, -1.0, 0.0),
+    'radiation_box_lb': (0.07, 0.04, -0.01),
+    'radiation_box_rt': (0.13, 0.06, 0.01),
+    'absorption_rate_0': 100.0,
+    'absorption_rate_1': 0.0,
+    'absorption_rate_2': 0.0,
+    'heat_enable': 0,
+    'linear_solver_heat': 'lu',
+    'heat_box_lb': (0.0, 0.0, 0.0),
+    'heat_box_rt': (0.0, 0.0, 0.0),
+    'conductivity_0': 1.0,
+    'conductivity_1': 1.0,
+    'conductivity_2': 1.0,
+    'temperature_initial': 0.0,
+    'heat_box_temperature': 0.0,
+    'heat_relaxation_factor': 1.0,
+    'time_second_order_heat': 1,
+    'incompressible_relaxation': 0.0,
+    'temperature_expansion_rate_0': 0.0,
+    'temperature_expansion_rate_1': 0.0,
+    'temperature_expansion_rate_2': 0.0,
+    'temperature_expansion_base_0': 0.0,
+    'temperature_expansion_base_1': 0.0,
+    'temperature_expansion_base_2': 0.0,
+    'fluid_enable': 1,
+    'advection_enable': 1,
+    'advection_solver': 'tvd',
+    'advection_dt_factor': 0.1,
+    'tvd_split': 0,
+    'convergence_tolerance': 0.01,
+    'num_iterations_limit': 10,
+    'velocity_relaxation_factor': 0.8,
+    'pressure_relaxation_factor': 0.9,
+    'linear_solver_velocity': 'lu',
+    'linear_solver_pressure': 'gauss_seidel',
+    'lu_relaxed_relaxation_factor': 1.9,
+    'lu_relaxed_num_iters_limit': 1000,
+    'lu_relaxed_tolerance': 0.001,
+    'time_second_order': 1,
+    'rhie_chow_factor': 1.0,
+    'simpler': 0,
+    'initial_volume_fraction_smooth_times': 2,
+    'density_smooth_times': 2,
+    'viscosity_smooth_times': 2,
+    'force_smooth_times': 0,
+    'force_geometric_average': 0,
+    'guess_extrapolation': 0.0,
+    'compressible_enable': 0,
+    'meshvel': (0.0, 0.0, 0.0),
+    'meshvel_output': 1,
+    'meshvel_weight': 0.5,
+    'sharp': 0.0,
+    'spawning_gap': 0.25,
+    'particle_radius': 1.5,
+    'min_num_particles': 3,
+    'max_num_particles': 10,
+    'back_relaxation_factor': 1.0,
+    'field_output_format': 'paraview',
+    'max_frame_index': 100,
+    'max_frame_scalar_index': 10000,
+    'no_output': 0,
+    'no_mesh_output': 0,
+    'SA_threshold': 0.0,
+    'stat_s_enable': 1,
+    'output_factor_x': 1,
+    'output_factor_y': 1,
+    'output_factor_z': 1,
+    'output_x': 1,
+    'output_y': 1,
+    'output_z': 0,
+    'output_velocity_x': 1,
+    'output_velocity_y': 1,
+    'output_velocity_z': 0,
+    'output_pressure': 1,
+    'output_density': 0,
+    'output_viscosity': 0,
+    'output_radiation': 0,
+    'output_temperature': 0,
+    'output_divergence': 0,
+    'output_mass_source_0': 0,
+    'output_mass_source_1': 0,
+    'output_mass_source_2': 0,
+    'output_mass_fraction_0': 0,
+    'output_mass_fraction_1': 0,
+    'output_mass_fraction_2': 0,
+    'output_volume_fraction_0': 1,
+    'output_volume_fraction_1': 1,
+    'output_volume_fraction_2': 0,
+    'output_density_0': 0,
+    'output_density_1': 0,
+    'output_density_2': 0,
+    'output_partial_density_0': 0,
+    'output_partial_density_1': 0,
+    'output_partial_density_2': 0,
+    'output_target_density_0': 0,
+    'output_target_density_1': 0,
+    'output_target_density_2': 0,
+    'output_volume_source': 0,
+    'output_curvature': 0,
+    'output_excluded': 0,
+    'iter_history_enable': 0,
+    'iter_history_mesh': 0,
+    'iter_history_n': 1,
+    'iter_history_sfixed': 0,
+}
+GENERAL_TYPES = {
+    'MODULE': 'string',
+    'plt_title': 'string',
+    'A': 'vect',
+    'B': 'vect',
+    'A1': 'vect',
+    'B1': 'vect',
+    'A2': 'vect',
+    'B2': 'vect',
+    'box_A': 'vect',
+    'box_B': 'vect',
+    'IC': 'vect',
+    'IR': 'double',
+    'IC2': 'vect',
+    'IR2': 'double',
+    'Nx': 'int',
+    'Ny': 'int',
+    'Nz': 'int',
+    'T': 'double',
+    'dt': 'double',
+    'dt_auto': 'bool',
+    'cfl': 'double',
+    'cfl_advection': 'double',
+    'num_phases': 'int',
+    'gravity': 'vect',
+    'force': 'vect',
+    'sigma': 'double',
+    'density_0': 'double',
+    'density_1': 'double',
+    'density_2': 'double',
+    'viscosity_0': 'double',
+    'viscosity_1': 'double',
+    'viscosity_2': 'double',
+    'molar_0': 'double',
+    'molar_1': 'double',
+    'molar_2': 'double',
+    'deforming_velocity': 'bool',
+    'initial_velocity': 'vect',
+    'condition_top': 'string',
+    'condition_bottom': 'string',
+    'condition_left': 'string',
+    'condition_right': 'string',
+    'condition_close': 'string',
+    'condition_far': 'string',
+    'chemistry': 'string',
+    'chem_intensity': 'double',
+    'reaction_zone_lb': 'vect',
+    'reaction_zone_rt': 'vect',
+    'radiation_enable': 'bool',
+    'radiation_intensity': 'double',
+    'radiation_direction': 'vect',
+    'radiation_box_lb': 'vect',
+    'radiation_box_rt': 'vect',
+    'absorption_rate_0': 'double',
+    'absorption_rate_1': 'double',
+    'absorption_rate_2': 'double',
+    'heat_enable': 'bool',
+    'linear_solver_heat': 'string',
+    'heat_box_lb': 'vect',
+    'heat_box_rt': 'vect',
+    'conductivity_0': 'double',
+    'conductivity_1': 'double',
+    'conductivity_2': 'double',
+    'temperature_initial': 'double',
+    'heat_box_temperature': 'double',
+    'heat_relaxation_factor': 'double',
+    'time_second_order_heat': 'bool',
+    'incompressible_relaxation': 'double',
+    'temperature_expansion_rate_0': 'double',
+    'temperature_expansion_rate_1': 'double',
+    'temperature_expansion_rate_2': 'double',
+    'temperature_expansion_base_0': 'double',
+    'temperature_expansion_base_1': 'double',
+    'temperature_expansion_base_2': 'double',
+    'fluid_enable': 'bool',
+    'advection_enable': 'bool',
+    'advection_solver': 'string',
+    'advection_dt_factor': 'double',
+    'tvd_split': 'bool',
+    'convergence_tolerance': 'double',
+    'num_iterations_limit': 'int',
+    'velocity_relaxation_factor': 'double',
+    'pressure_relaxation_factor': 'double',
+    'linear_solver_velocity': 'string',
+    'linear_solver_pressure': 'string',
+    'lu_relaxed_relaxation_factor': 'double',
+    'lu_relaxed_num_iters_limit': 'int',
+    'lu_relaxed_tolerance': 'double',
+    'time_second_order': 'bool',
+    'rhie_chow_factor': 'double',
+    'simpler': 'bool',
+    'initial_volume_fraction_smooth_times': 'int',
+    'density_smooth_times': 'int',
+    'viscosity_smooth_times': 'int',
+    'force_smooth_times': 'int',
+    'force_geometric_average': 'bool',
+    'guess_extrapolation': 'double',
+    'compressible_enable': 'bool',
+    'meshvel': 'vect',
+    'meshvel_output': 'bool',
+    'meshvel_weight': 'double',
+    'sharp': 'double',
+    'spawning_gap': 'double',
+    'particle_radius': 'double',
+    'min_num_particles': 'int',
+    'max_num_particles': 'int',
+    'back_relaxation_factor': 'double',
+    'field_output_format': 'string',
+    'max_frame_index': 'int',
+    'max_frame_scalar_index': 'int',
+    'no_output': 'bool',
+    'no_mesh_output': 'bool',
+    'SA_threshold': 'double',
+    'stat_s_enable': 'bool',
+    'output_factor_x': 'int',
+    'output_factor_y': 'int',
+    'output_factor_z': 'int',
+    'output_x': 'bool',
+    'output_y': 'bool',
+    'output_z': 'bool',
+    'output_velocity_x': 'bool',
+    'output_velocity_y': 'bool',
+    'output_velocity_z': 'bool',
+    'output_pressure': 'bool',
+    'output_density': 'bool',
+    'output_viscosity': 'bool',
+    'output_radiation': 'bool',
+    'output_temperature': 'bool',
+    'output_divergence': 'bool',
+    'output_mass_source_0': 'bool',
+    'output_mass_source_1': 'bool',
+    'output_mass_source_2': 'bool',
+    'output_mass_fraction_0': 'bool',
+    'output_mass_fraction_1': 'bool',
+    'output_mass_fraction_2': 'bool',
+    'output_volume_fraction_0': 'bool',
+    'output_volume_fraction_1': 'bool',
+    'output_volume_fraction_2': 'bool',
+    'output_density_0': 'bool',
+    'output_density_1': 'bool',
+    'output_density_2': 'bool',
+    'output_partial_density_0': 'bool',
+    'output_partial_density_1': 'bool',
+    'output_partial_density_2': 'bool',
+    'output_target_density_0': 'bool',
+    'output_target_density_1': 'bool',
+    'output_target_density_2': 'bool',
+    'output_volume_source': 'bool',
+    'output_curvature': 'bool',
+    'output_excluded': 'bool',
+    'iter_history_enable': 'bool',
+    'iter_history_mesh': 'bool',
+    'iter_history_n': 'int',
+    'iter_history_sfixed': 'int',
 }
 
 MODULE_DIM = {"hydro2D_uniform_MPI": 2, "hydro2d": 2, "hydro3D_uniform_MPI": 3, "hydro3d": 3,
@@ -200,7 +487,7 @@ class Params(dict):
         for name in ("initial_volume_fraction_smooth_times", "dt_auto", "fluid_enable", "advection_enable",
                      "num_iterations_limit", "time_second_order", "simpler", "force_geometric_average",
                      "lu_relaxed_num_iters_limit", "density_smooth_times", "viscosity_smooth_times",
-                     "force_smooth_times", "tvd_split", "heat_enable", "time_second_order_heat"):
+                     "force_smooth_times", "tvd_split", "heat_enable", "time_second_order_heat", "meshvel_output"):
             setattr(c, name, int(need(name)))
         for name in ("dt", "cfl", "cfl_advection", "sigma", "convergence_tolerance", "velocity_relaxation_factor",
                      "pressure_relaxation_factor", "rhie_chow_factor", "guess_extrapolation",
@@ -231,14 +518,16 @@ class Params(dict):
                 out.append('set string %s "%s"' % (k, v) if " " in v else "set string %s %s" % (k, v))
             elif isinstance(v, (tuple, list)):
                 out.append("set vect %s (%s)" % (k, ", ".join(repr(float(x)) for x in v)))
-            elif isinstance(v, float):
-                out.append("set double %s %r" % (k, v))
+            elif isinstance(v, float) or k in _DOUBLE_KEYS or GENERAL_TYPES.get(k) == "double":
+                out.append("set double %s %r" % (k, float(v)))
             else:
-                typ = "bool" if k in _BOOL_KEYS else "int"
+                typ = "bool" if (k in _BOOL_KEYS or GENERAL_TYPES.get(k) == "bool") else "int"
                 out.append("set %s %s %d" % (typ, k, int(v)))
         return out
 
 
+_DOUBLE_KEYS = {"initial_sin_lambda", "initial_sin_phase", "pressure_fixed_value", "T", "dt",
+                "initial_volume_fraction_0", "initial_volume_fraction_1", "initial_volume_fraction_2"}
 _BOOL_KEYS = {"dt_auto", "deforming_velocity", "radiation_enable", "heat_enable", "time_second_order_heat",
               "fluid_enable", "advection_enable", "tvd_split", "time_second_order", "simpler",
               "force_geometric_average", "compressible_enable", "initial_pois", "no_output", "no_mesh_output"}

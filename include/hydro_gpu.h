@@ -120,6 +120,7 @@ typedef struct hg_config {
   int time_second_order, simpler, force_geometric_average;
   double guess_extrapolation;
   double meshvel[3];
+  int meshvel_output;              /* CalcStat adds meshpos += meshvel*dt (hydro2d.hpp:1526-1528) */
   int linear_solver_velocity, linear_solver_pressure, linear_solver_heat; /* hg_linear_solver */
   double lu_relaxed_tolerance;
   int lu_relaxed_num_iters_limit;

@@ -60,7 +60,7 @@ struct ho_state {
   int last_sweeps_total; double last_diff;
   int nres; double res_hist[4096];
   hg_step_stats stat;
-  int have_stat_cx; double prev_cx[HG_MAX_PHASES];
+  double meshpos[3];
   char err[256];
 };
 
@@ -797,8 +797,9 @@ int ho_calc_stat(ho_handle s, hg_step_stats* st) {                   /* hydro2d.
     }
     st->volume[i] = volume; st->mass[i] = volume * s->cfg.density[i];
     st->pd_min[i] = pmin; st->pd_max[i] = pmax;
-    for (int d = 0; d < 3; ++d) { st->center[i][d] = d < s->dim ? cen[d] / volume : 0.; st->velocity[i][d] = d < s->dim ? vel[d] / volume : 0.; }
+    for (int d = 0; d < 3; ++d) { st->center[i][d] = d < s->dim ? cen[d] / volume + s->meshpos[d] : 0.; st->velocity[i][d] = d < s->dim ? vel[d] / volume : 0.; }
   }
+  if (s->cfg.meshvel_output) for (int d = 0; d < s->dim; ++d) s->meshpos[d] += s->cfg.meshvel[d] * s->dt; /* :1526-1528 */
   return 0;
 }
 
@@ -861,7 +862,7 @@ void ho_config_defaults(hg_config* c) {          /* examples/general.hydroconf *
   c->lu_relaxed_relaxation_factor = 1.9; c->lu_relaxed_num_iters_limit = 1000; c->lu_relaxed_tolerance = 1e-3;
   c->time_second_order = 1; c->rhie_chow_factor = 1.;
   c->initial_volume_fraction_smooth_times = 2; c->density_smooth_times = 2; c->viscosity_smooth_times = 2;
-  c->heat_relaxation_factor = 1.; c->time_second_order_heat = 1;
+  c->heat_relaxation_factor = 1.; c->time_second_order_heat = 1; c->meshvel_output = 1;
   c->world_size = 1;
 }
 
