@@ -455,7 +455,7 @@ class Params(dict):
         if module not in MODULE_DIM:
             raise ValueError("Unknown module '%s'" % module)
         c.dim = MODULE_DIM[module]
-        c.Nx, c.Ny, c.Nz = int(need("Nx")), int(need("Ny")), int(need("Nz")) if c.dim == 3 else 1
+        c.Nx, c.Ny, c.Nz = int(need("Nx")), int(need("Ny")), int(need("Nz"))  # Nz ignored for dim == 2
         for name in ("A", "B", "box_A", "box_B", "A1", "B1", "A2", "B2", "IC", "IC2", "gravity", "force",
                      "meshvel", "heat_box_lb", "heat_box_rt"):
             setattr(c, name, d3(*_vec3(need(name))))
@@ -479,10 +479,12 @@ class Params(dict):
             c.initial_sin_lambda = float(need("initial_sin_lambda"))
             c.initial_sin_phase = float(need("initial_sin_phase"))
         c.num_phases = int(need("num_phases"))
-        for i in range(min(c.num_phases, HG_MAX_PHASES)):
-            c.density[i] = float(need("density_%d" % i))
-            c.viscosity[i] = float(need("viscosity_%d" % i))
-            c.conductivity[i] = float(need("conductivity_%d" % i))
+        for i in range(HG_MAX_PHASES):
+            if i < c.num_phases:
+                need("density_%d" % i), need("viscosity_%d" % i), need("conductivity_%d" % i)
+            c.density[i] = float(p.get("density_%d" % i, 1.0))
+            c.viscosity[i] = float(p.get("viscosity_%d" % i, 1.0))
+            c.conductivity[i] = float(p.get("conductivity_%d" % i, 1.0))
             c.initial_volume_fraction[i] = float(p.get("initial_volume_fraction_%d" % i, 0.0))
         for name in ("initial_volume_fraction_smooth_times", "dt_auto", "fluid_enable", "advection_enable",
                      "num_iterations_limit", "time_second_order", "simpler", "force_geometric_average",

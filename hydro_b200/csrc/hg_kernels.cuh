@@ -1,0 +1,672 @@
+// hg_kernels.cuh -- CUDA kernels of the per-time-step path (sm_100a, fp64, -fmad=false).
+//
+// One thread per cell, x fastest (coalesced 8-byte loads along i); face quantities are
+// recomputed from cell values instead of being stored as face fields (the reference
+// materialises a FieldFace for every Interpolate call).  Each kernel cites the reference
+// code it replaces; the arithmetic order follows oracle/hydro_oracle.c.
+#pragma once
+#include <cooperative_groups.h>
+#include "hg_device.cuh"
+
+namespace cg = cooperative_groups;
+
+#define CELL_LOOP_PROLOG(g)                                                   \
+  long long c_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;            \
+  long long nc_ = (long long)(g).n[0] * (g).n[1] * (g).n[2];                  \
+  if (c_ >= nc_) return;                                                      \
+  int i = (int)(c_ % (g).n[0]);                                               \
+  int j = (int)((c_ / (g).n[0]) % (g).n[1]);                                  \
+  int k = (int)(c_ / ((long long)(g).n[0] * (g).n[1]));                       \
+  const long long c = c_;
+
+struct P3 { double* p[3]; };
+struct CP3 { const double* p[3]; };
+struct P9 { double* p[9]; };
+struct P7 { double* p[7]; };
+
+// ---------------------------------------------------------------- small utilities
+__global__ void k_fill(double* a, double v, long long n) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) a[t] = v;
+}
+// StartStep: iter_curr = time_curr + (time_curr - time_prev) * guess_extrapolation
+// (fluid.hpp:800-811, conv_diff.hpp:123-128)
+__global__ void k_start_layer(double* __restrict__ ic, const double* __restrict__ tc,
+                              const double* __restrict__ tp, double ge, long long n) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) ic[t] = tc[t] + (tc[t] - tp[t]) * ge;
+}
+// IsNan scan (solver.hpp:17-30): sets *flag when !(a*0 == 0)
+__global__ void k_nan_flag(const double* __restrict__ a, long long n, int* flag) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n && !(a[t] * 0. == 0.)) *flag = 1;
+}
+
+// ---------------------------------------------------------------- GetSmoothField
+// One repeat of Average(Interpolate(u, zero-derivative)) (solver.hpp:621-656)
+template <int DIM>
+__global__ void k_smooth(Geo g, const double* __restrict__ u, double* __restrict__ out) {
+  CELL_LOOP_PROLOG(g)
+  double sum = 0.;
+#pragma unroll
+  for (int q = 0; q < 2 * DIM; ++q) {
+    int d = q >> 1, o = q & 1;
+    sum += face_value<DIM, K_NEUMANN0>(g, u, d, i + (d == 0 ? o : 0), j + (d == 1 ? o : 0), k + (d == 2 ? o : 0), 0);
+  }
+  out[c] = sum / (double)(2 * DIM);
+}
+
+// Gradient(Interpolate(u, cond)) for hg_interp_grad
+template <int DIM, int KIND>
+__global__ void k_interp_grad(Geo g, const double* __restrict__ u, int aux, P3 out) {
+  CELL_LOOP_PROLOG(g)
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) out.p[d][c] = cell_grad<DIM, KIND>(g, u, d, i, j, k, aux);
+}
+
+// ---------------------------------------------------------------- fluid properties
+// CalcPhasesVolumeFraction + GetVolumeAveraged (hydro2d.hpp:981-997, 1235-1246)
+struct PropArgs {
+  int np; double density[3], viscosity[3], conductivity[3];
+  const double* pd[3]; double* vf[3]; double* rho_raw; double* mu_raw; double* kc;
+};
+__global__ void k_volfrac(PropArgs a, long long n) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  double v[3]; double sum = 0.;
+  for (int p = 0; p < a.np; ++p) { v[p] = a.pd[p][c] / a.density[p]; sum += v[p]; }
+  double r = 0., m = 0., kk = 0.;
+  for (int p = 0; p < a.np; ++p) {
+    v[p] /= sum; a.vf[p][c] = v[p];
+    r += a.density[p] * v[p]; m += a.viscosity[p] * v[p]; kk += a.conductivity[p] * v[p];
+  }
+  a.rho_raw[c] = r; a.mu_raw[c] = m; a.kc[c] = kk;
+}
+// fc_force = gravity * fc_density + force (hydro2d.hpp:1308-1314)
+__global__ void k_force(int dim, const double* __restrict__ rho_raw, double gx, double gy, double gz,
+                        double fx, double fy, double fz, P3 out, long long n) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  out.p[0][c] = fx + gx * rho_raw[c];
+  out.p[1][c] = fy + gy * rho_raw[c];
+  if (dim > 2) out.p[2][c] = fz + gz * rho_raw[c];
+}
+// surface tension force (hydro2d.hpp:1318-1370); gs = Gradient(Interpolate(vf1, pd cond of phase 0))
+template <int DIM>
+__global__ void k_stforce(Geo g, CP3 gs, double sigma, P3 out) {
+  CELL_LOOP_PROLOG(g)
+  double fv[3] = {0., 0., 0.};
+#pragma unroll
+  for (int q = 0; q < 2 * DIM; ++q) {
+    int qd = q >> 1, o = q & 1;
+    int fi = i + (qd == 0 ? o : 0), fj = j + (qd == 1 ? o : 0), fk = k + (qd == 2 ? o : 0);
+    double gv[3] = {0., 0., 0.}, nn[3] = {0., 0., 0.};
+    double sq = 0.;
+    for (int d = 0; d < DIM; ++d) { gv[d] = face_value<DIM, K_NEUMANN0>(g, gs.p[d], qd, fi, fj, fk, 0); sq += gv[d] * gv[d]; }
+    double nrm = sqrt(sq);
+    for (int d = 0; d < DIM; ++d) nn[d] = gv[d] / (nrm + 1e-6);
+    double so[3] = {0., 0., 0.}; so[qd] = g.area[qd] * (o ? 1. : -1.);
+    double sdn = 0.; for (int d = 0; d < DIM; ++d) sdn += so[d] * nn[d];
+    for (int d = 0; d < DIM; ++d) { fv[d] += gv[d] * sdn; fv[d] -= so[d] * nrm; }
+  }
+  for (int d = 0; d < DIM; ++d) { fv[d] /= g.vol; out.p[d][c] = fv[d] * sigma; }
+}
+template <int DIM>
+__global__ void k_grad_pd(Geo g, const double* __restrict__ u, const double* __restrict__ pdinit, P3 out) {
+  CELL_LOOP_PROLOG(g)
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) out.p[d][c] = cell_grad<DIM, K_PD>(g, u, d, i, j, k, 0, pdinit);
+}
+
+// ---------------------------------------------------------------- SIMPLE iteration kernels
+// K_pre: restored external force (CalcExtForce, fluid.hpp:602-631) and pressure gradient
+// Gradient(Interpolate(p_prev, extrapolation)) (fluid.hpp:827-829)
+template <int DIM>
+__global__ void k_pre(Geo g, CP3 force, const double* __restrict__ pprev, P3 fcr, P3 gp) {
+  CELL_LOOP_PROLOG(g)
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    double sum = 0.;
+    double fm = face_value<DIM, K_NEUMANN0>(g, force.p[d], d, i, j, k, 0);
+    double fp = face_value<DIM, K_NEUMANN0>(g, force.p[d], d, i + (d == 0), j + (d == 1), k + (d == 2), 0);
+    sum += (g.area[d] * fm) * (0.5 * g.h[d]);
+    sum += (g.area[d] * fp) * (0.5 * g.h[d]);
+    fcr.p[d][c] = sum / g.vol;
+    gp.p[d][c] = cell_grad<DIM, K_EXTRAP>(g, pprev, d, i, j, k, 0);
+  }
+}
+
+// K_velgrad: G[n*DIM+d] = d-component of Gradient(Interpolate(u_n, wall velocity)) -- used by the
+// explicit viscous term (fluid.hpp:838-843) and by the deferred upwind correction (conv_diff.hpp:135)
+template <int DIM>
+__global__ void k_velgrad(Geo g, CP3 u, P9 G) {
+  CELL_LOOP_PROLOG(g)
+#pragma unroll
+  for (int n = 0; n < DIM; ++n)
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) G.p[n * DIM + d][c] = cell_grad<DIM, K_VEL>(g, u.p[n], d, i, j, k, n);
+}
+
+struct P9c { const double* p[9]; };
+
+// K_source: momentum source = explicit viscous term + (-grad p + restored force + surface tension)
+// (fluid.hpp:835-870)
+template <int DIM>
+__global__ void k_source(Geo g, P9c G, const double* __restrict__ mu, CP3 gp, CP3 fcr, CP3 stf, int use_stf, P3 fs) {
+  CELL_LOOP_PROLOG(g)
+  double acc[3] = {0., 0., 0.};
+#pragma unroll
+  for (int n = 0; n < DIM; ++n) {
+    int mi = i, mj = j, mk = k;
+    int pi = i + (n == 0), pj = j + (n == 1), pk = k + (n == 2);
+    double mum = face_value<DIM, K_NEUMANN0>(g, mu, n, mi, mj, mk, 0);
+    double mup = face_value<DIM, K_NEUMANN0>(g, mu, n, pi, pj, pk, 0);
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      double gm = face_value<DIM, K_NEUMANN0>(g, G.p[n * DIM + d], n, mi, mj, mk, 0);
+      double gq = face_value<DIM, K_NEUMANN0>(g, G.p[n * DIM + d], n, pi, pj, pk, 0);
+      double sum = 0.;
+      sum += gm * (mum * (g.area[n] * -1.));
+      sum += gq * (mup * (g.area[n] * 1.));
+      acc[d] += sum / g.vol;
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    double st = use_stf ? stf.p[d][c] : 0.;
+    double t = ((gp.p[d][c] * (-1.) + fcr.p[d][c]) + st) + 0.;  // + u*(rho*q_vol - q_mass), sources are zero
+    fs.p[d][c] = acc[d] + t;
+  }
+}
+
+// K_assemble: ConvectionDiffusionScalarImplicit::MakeIteration assembly (conv_diff.hpp:149-227) for
+// NCOMP scalars sharing one coefficient matrix (the dim velocity components, or the temperature).
+// Writes the 7-coefficient rows and the delta-form constants in the hyperplane-major layout used by
+// the ordered sweeps, and Expression::CoeffSum (fluid.hpp:876-883).
+struct AsmArgs {
+  const double* prev[3];   // iter_prev = field the iteration starts from
+  const double* tc[3];     // time_curr
+  const double* tp[3];     // time_prev
+  const double* src[3];
+  const double* grad[9];   // G[n*DIM+d] (only d == face direction is read)
+  const double* rho;       // nullptr = 1 (heat.hpp:31)
+  const double* mu;        // cell diffusion rate, faces by zero-derivative interpolation
+  const double* F;         // volume flux (face field)
+  double co[3];            // BDF coefficients (solver.hpp:816-861)
+  double relax;
+  double* A[7];            // sheared
+  double* R[3];            // sheared
+  double* coeffsum;        // natural, nullable
+  double coeffsum_div;     // dim
+};
+template <int DIM, int KIND, int NCOMP>
+__global__ void k_assemble(Geo g, AsmArgs a) {
+  CELL_LOOP_PROLOG(g)
+  const long long cs = shidx(g, i, j, k);
+  if (cell_excl(g, i, j, k)) {   // conv_diff.hpp:222-226
+#pragma unroll
+    for (int t = 0; t < 7; ++t) if (DIM > 2 || (t != CZM && t != CZP)) a.A[t][cs] = (t == CD) ? 1. : 0.;
+    for (int n = 0; n < NCOMP; ++n) a.R[n][cs] = 0.;
+    if (a.coeffsum) { double s = 0.; for (int n = 0; n < NCOMP; ++n) s += 1.; a.coeffsum[c] = s / a.coeffsum_div; }
+    return;
+  }
+  const int tmap[6] = {CXM, CXP, CYM, CYP, CZM, CZP};
+  const long long off[7] = {-g.sz, -g.sy, -1, 0, 1, g.sy, g.sz};
+  double cdiag = 0., ddiag = 0.;
+  bool have_c = false, have_d = false;
+  double cn[6] = {0, 0, 0, 0, 0, 0}, dn[6] = {0, 0, 0, 0, 0, 0};
+  bool present[6] = {false, false, false, false, false, false};
+  double cconst[NCOMP], dconst[NCOMP];
+#pragma unroll
+  for (int n = 0; n < NCOMP; ++n) { cconst[n] = 0.; dconst[n] = 0.; }
+#pragma unroll
+  for (int q = 0; q < 2 * DIM; ++q) {
+    const int d = q >> 1, o = q & 1;
+    const double sgn = o ? 1. : -1.;
+    const int fi = i + (d == 0 ? o : 0), fj = j + (d == 1 ? o : 0), fk = k + (d == 2 ? o : 0);
+    FaceInfo f = face_info<DIM>(g, d, fi, fj, fk);
+    if (f.type == FT_EXCL) continue;
+    const double Ff = a.F[fidx(g, d, fi, fj, fk)];
+    if (f.type == FT_INNER) {
+      const double muf = a.mu[f.cm] * (1. - 0.5) + a.mu[f.cp] * 0.5;
+      double vm, vp;
+      int up;  // 0: cm upwind, 1: cp upwind, 2: central  (solver.hpp:223-242, threshold 1e-10)
+      if (Ff > 1e-10) { vm = 1.; vp = 0.; up = 0; }
+      else if (Ff < -1e-10) { vm = 0.; vp = 1.; up = 1; }
+      else { vm = 0.5; vp = 0.5; up = 2; }
+      const double alpha = 1. / g.h[d];
+      const double dm = ((-alpha) * (-muf)) * g.area[d];
+      const double dp = ((alpha) * (-muf)) * g.area[d];
+      double cself, cnb, dself, dnb;
+      if (o) { cself = vm * Ff; cnb = vp * Ff; dself = dm; dnb = dp; }
+      else { cself = vp * Ff; cnb = vm * Ff; dself = dp; dnb = dm; }
+      cself *= sgn; cnb *= sgn; dself *= sgn; dnb *= sgn;
+      cdiag = have_c ? cdiag + cself : cself; have_c = true;
+      ddiag = have_d ? ddiag + dself : dself; have_d = true;
+      cn[q] = cnb; dn[q] = dnb; present[q] = true;
+#pragma unroll
+      for (int n = 0; n < NCOMP; ++n) {
+        double vc = 0.;
+        if (up == 0) vc = -(a.grad[n * DIM + d][f.cm] * (-0.5 * g.h[d]));
+        else if (up == 1) vc = -(a.grad[n * DIM + d][f.cp] * (0.5 * g.h[d]));
+        cconst[n] += (vc * Ff) * sgn;
+        dconst[n] += ((0. * (-muf)) * g.area[d]) * sgn;
+      }
+    } else {
+      // boundary face (solver.hpp:258-280, 318-340)
+      const double muf = a.mu[c];
+      const double factor = o ? 1. : -1.;   // id == 0 for a plus face
+      bool dirichlet = false;
+      if (KIND == K_VEL) dirichlet = true;
+      else if (KIND == K_TEMP) dirichlet = face_temp_dirichlet<DIM>(g, d, fi, fj, fk);
+      if (dirichlet) {
+        const double alpha = 1. / (0.5 * g.h[d]) * factor;
+        const double dself = (((-alpha) * (-muf)) * g.area[d]) * sgn;
+        ddiag = have_d ? ddiag + dself : dself; have_d = true;
+#pragma unroll
+        for (int n = 0; n < NCOMP; ++n) {
+          const double val = (KIND == K_VEL) ? g.bcvel[f.side][n] : g.heat_T;
+          cconst[n] += (val * Ff) * sgn;
+          dconst[n] += (((alpha * val) * (-muf)) * g.area[d]) * sgn;
+        }
+      } else {
+        const double alpha = (0.5 * g.h[d]) * factor;
+        const double cself = (1. * Ff) * sgn;
+        cdiag = have_c ? cdiag + cself : cself; have_c = true;
+#pragma unroll
+        for (int n = 0; n < NCOMP; ++n) {
+          cconst[n] += ((alpha * 0.) * Ff) * sgn;
+          dconst[n] += ((0. * (-muf)) * g.area[d]) * sgn;
+        }
+      }
+    }
+  }
+  const double r = a.rho ? a.rho[c] : 1.;
+  double coef[7] = {0, 0, 0, 0, 0, 0, 0};
+  coef[CD] = ((have_c ? cdiag / g.vol : 0.) + a.co[2]) * r + (have_d ? ddiag / g.vol : 0.);
+#pragma unroll
+  for (int q = 0; q < 2 * DIM; ++q) if (present[q]) coef[tmap[q]] = (cn[q] / g.vol) * r + dn[q] / g.vol;
+  // delta form: constant := eqn.Evaluate(prev) in ascending index order (conv_diff.hpp:218)
+#pragma unroll
+  for (int n = 0; n < NCOMP; ++n) {
+    const double uconst = a.co[0] * a.tp[n][c] + a.co[1] * a.tc[n][c];
+    double ev = ((cconst[n] / g.vol + uconst) * r + dconst[n] / g.vol) - a.src[n][c];
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+      if (DIM == 2 && (t == CZM || t == CZP)) continue;
+      if (t == CD) { ev += a.prev[n][c] * coef[CD]; continue; }
+      const int q = (t == CXM) ? 0 : (t == CXP) ? 1 : (t == CYM) ? 2 : (t == CYP) ? 3 : (t == CZM) ? 4 : 5;
+      if (present[q]) ev += a.prev[n][c + off[t]] * coef[t];
+    }
+    a.R[n][cs] = ev;
+  }
+  coef[CD] /= a.relax;   // conv_diff.hpp:221
+  if (a.coeffsum) {
+    double csum = 0.;
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+      if (DIM == 2 && (t == CZM || t == CZP)) continue;
+      if (t == CD) { csum += coef[CD]; continue; }
+      const int q = (t == CXM) ? 0 : (t == CXP) ? 1 : (t == CYM) ? 2 : (t == CYP) ? 3 : (t == CZM) ? 4 : 5;
+      if (present[q]) csum += coef[t];
+    }
+    double s = 0.;
+    for (int n = 0; n < NCOMP; ++n) s += csum;   // fluid.hpp:878-882
+    a.coeffsum[c] = s / a.coeffsum_div;
+  }
+#pragma unroll
+  for (int t = 0; t < 7; ++t) if (DIM > 2 || (t != CZM && t != CZP)) a.A[t][cs] = coef[t];
+}
+
+// u_curr = u_prev + corr (conv_diff.hpp:246-248); corr is in the sheared layout
+template <int DIM, int NCOMP>
+__global__ void k_apply_corr(Geo g, CP3 prev, CP3 X, P3 curr) {
+  CELL_LOOP_PROLOG(g)
+  const long long cs = shidx(g, i, j, k);
+#pragma unroll
+  for (int n = 0; n < NCOMP; ++n) curr.p[n][c] = prev.p[n][c] + X.p[n][cs];
+}
+
+// K_fstar: Rhie-Chow volume flux (fluid.hpp:903-940).  One thread per cell computes the cell's
+// minus faces, plus the plus face where the cell is the last one in that direction.
+struct FstarArgs {
+  const double* us[3]; const double* gp[3]; const double* fcr[3]; const double* force[3];
+  const double* pprev; const double* dc; double rc; double meshvel[3]; double* Fs;
+};
+template <int DIM>
+DV double fstar_face(const Geo& g, const FstarArgs& a, int d, int fi, int fj, int fk) {
+  FaceInfo f = face_info<DIM>(g, d, fi, fj, fk);
+  const double A = g.area[d];
+  const double mv = a.meshvel[d] * A;
+  if (f.type == FT_INNER) {
+    const double ffu = a.us[d][f.cm] * (1. - 0.5) + a.us[d][f.cp] * 0.5;
+    const double vfi = ffu * A;
+    const double fgp = a.gp[d][f.cm] * (1. - 0.5) + a.gp[d][f.cp] * 0.5;
+    const double ffr = a.fcr[d][f.cm] * (1. - 0.5) + a.fcr[d][f.cp] * 0.5;
+    const double ffe = a.force[d][f.cm] * (1. - 0.5) + a.force[d][f.cp] * 0.5;
+    const double dfc = a.dc[f.cm] * (1. - 0.5) + a.dc[f.cp] * 0.5;
+    const double wide = (fgp - ffr) * A;
+    const double compact = (a.pprev[f.cp] - a.pprev[f.cm]) / g.h[d] * A - ffe * A;
+    return (vfi + a.rc * (wide - compact) / dfc + 0) - mv;
+  }
+  const double ffu = (f.type == FT_BOUND) ? g.bcvel[f.side][d] : 0.;
+  return ffu * A - mv;
+}
+template <int DIM>
+__global__ void k_fstar(Geo g, FstarArgs a) {
+  CELL_LOOP_PROLOG(g)
+  (void)c;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    a.Fs[fidx(g, d, i, j, k)] = fstar_face<DIM>(g, a, d, i, j, k);
+    const int x = d == 0 ? i : (d == 1 ? j : k);
+    if (x == g.n[d] - 1) {
+      const int fi = i + (d == 0), fj = j + (d == 1), fk = k + (d == 2);
+      a.Fs[fidx(g, d, fi, fj, fk)] = fstar_face<DIM>(g, a, d, fi, fj, fk);
+    }
+  }
+}
+
+// face coefficient c_f = A / (h * d_f) of the flux-correction expression (fluid.hpp:957-964)
+template <int DIM>
+DV double face_coeff(const Geo& g, const double* __restrict__ dc, int d, const FaceInfo& f) {
+  const double dfc = dc[f.cm] * (1. - 0.5) + dc[f.cp] * 0.5;
+  const double coeff = -g.area[d] / (g.h[d] * dfc);
+  return -coeff;
+}
+
+// K_prhs: constants of the pressure-correction rows (fluid.hpp:972-1014) and the diagonal field in
+// the sheared layout; the sweep kernels regenerate the off-diagonals A/(h d_f) from it.
+template <int DIM>
+__global__ void k_prhs(Geo g, const double* __restrict__ Fs, const double* __restrict__ dc,
+                       double* __restrict__ RP, double* __restrict__ D) {
+  CELL_LOOP_PROLOG(g)
+  const long long cs = shidx(g, i, j, k);
+  D[cs] = dc[c];
+  if (cell_excl(g, i, j, k)) { RP[cs] = 0.; return; }
+  if (c == g.pfix) { RP[cs] = -g.pfix_value; return; }
+  double cst = 0.;
+  double extra = 0.; bool has_extra = false;
+#pragma unroll
+  for (int q = 0; q < 2 * DIM; ++q) {
+    const int d = q >> 1, o = q & 1;
+    const int fi = i + (d == 0 ? o : 0), fj = j + (d == 1 ? o : 0), fk = k + (d == 2 ? o : 0);
+    cst += Fs[fidx(g, d, fi, fj, fk)] * (o ? 1. : -1.);
+  }
+  double rhs = cst + -(0. * g.vol);
+  if (g.pfix >= 0) {
+    // SetKnownValue (linear.hpp:238-250): rows coupling to the fixed cell get value*coeff added, in
+    // ascending order of the fixed cell's neighbours (fluid.hpp:1002-1011 loops over all cells once)
+#pragma unroll
+    for (int q = 0; q < 2 * DIM; ++q) {
+      const int d = q >> 1, o = q & 1;
+      const int ni = i + (d == 0 ? (o ? 1 : -1) : 0), nj = j + (d == 1 ? (o ? 1 : -1) : 0), nk = k + (d == 2 ? (o ? 1 : -1) : 0);
+      if (!cell_in(g, ni, nj, nk) || cidx(g, ni, nj, nk) != g.pfix) continue;
+      const int fi = i + (d == 0 ? o : 0), fj = j + (d == 1 ? o : 0), fk = k + (d == 2 ? o : 0);
+      FaceInfo f = face_info<DIM>(g, d, fi, fj, fk);
+      if (f.type != FT_INNER) continue;
+      const double cf = face_coeff<DIM>(g, dc, d, f);
+      extra = g.pfix_value * (-cf); has_extra = true;
+    }
+  }
+  (void)has_extra;
+  RP[cs] = (g.pfix >= 0 && has_extra) ? rhs + extra : rhs;
+}
+
+// K_pcorr: p' back to the natural layout, p_curr = p_prev + alpha_p p' (fluid.hpp:1035-1038)
+template <int DIM>
+__global__ void k_pcorr(Geo g, const double* __restrict__ PP, const double* __restrict__ pprev, double alpha,
+                        double* __restrict__ pc, double* __restrict__ pcurr) {
+  CELL_LOOP_PROLOG(g)
+  const double v = PP[shidx(g, i, j, k)];
+  pc[c] = v;
+  pcurr[c] = pprev[c] + alpha * v;
+}
+
+// K_correct: velocity correction u += -grad p' / d_c (fluid.hpp:1040-1050) and the divergence-free
+// fluxes F = F* + c_f (p'_m - p'_p) (fluid.hpp:1053-1056)
+struct CorrArgs { const double* pc; const double* dc; const double* Fs; double* u[3]; double* F; };
+template <int DIM>
+DV double fcorr_face(const Geo& g, const CorrArgs& a, int d, int fi, int fj, int fk) {
+  const long long fx = fidx(g, d, fi, fj, fk);
+  double r = a.Fs[fx];
+  FaceInfo f = face_info<DIM>(g, d, fi, fj, fk);
+  if (f.type == FT_INNER) {
+    const double cf = face_coeff<DIM>(g, a.dc, d, f);
+    r += a.pc[f.cm] * cf;
+    r += a.pc[f.cp] * (-cf);
+  }
+  return r;
+}
+template <int DIM>
+__global__ void k_correct(Geo g, CorrArgs a) {
+  CELL_LOOP_PROLOG(g)
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    const double gpc = cell_grad<DIM, K_EXTRAP>(g, a.pc, d, i, j, k, 0);
+    a.u[d][c] += gpc / (-a.dc[c]);
+    a.F[fidx(g, d, i, j, k)] = fcorr_face<DIM>(g, a, d, i, j, k);
+    const int x = d == 0 ? i : (d == 1 ? j : k);
+    if (x == g.n[d] - 1) {
+      const int fi = i + (d == 0), fj = j + (d == 1), fk = k + (d == 2);
+      a.F[fidx(g, d, fi, fj, fk)] = fcorr_face<DIM>(g, a, d, fi, fj, fk);
+    }
+  }
+}
+
+// K_resid: CalcDiff of vector fields, max_c ||a - b||_2 (solver.hpp:804-813)
+template <int DIM>
+__global__ void k_resid(CP3 ic, CP3 ip, long long n, double* out) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.;
+  if (c < n) {
+    double sq = 0.;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) { double e = ip.p[d][c] - ic.p[d][c]; sq += e * e; }
+    v = sqrt(sq);
+    if (!(v == v)) v = 0.;   // std::max(res, NaN) keeps res
+  }
+  v = warp_max(v);
+  __shared__ double sm[32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.;
+    v = warp_max(v);
+    if (threadIdx.x == 0) atomic_max_nonneg(out, v);
+  }
+}
+
+// GetAutoTimeStep: min over non-excluded cells and their faces of |V / F|, F != 0 (fluid.hpp:1191-1206)
+template <int DIM>
+__global__ void k_auto_dt(Geo g, const double* __restrict__ F, double* out) {
+  long long c_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long nc_ = (long long)g.n[0] * g.n[1] * g.n[2];
+  double v = 1e10;
+  if (c_ < nc_) {
+    int i = (int)(c_ % g.n[0]); int j = (int)((c_ / g.n[0]) % g.n[1]); int k = (int)(c_ / ((long long)g.n[0] * g.n[1]));
+    if (!cell_excl(g, i, j, k)) {
+#pragma unroll
+      for (int q = 0; q < 2 * DIM; ++q) {
+        const int d = q >> 1, o = q & 1;
+        const double fl = F[fidx(g, d, i + (d == 0 ? o : 0), j + (d == 1 ? o : 0), k + (d == 2 ? o : 0))];
+        if (fl != 0.) v = smin(v, fabs(g.vol / fl));
+      }
+    }
+  }
+  v = warp_min(v);
+  __shared__ double sm[32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 1e10;
+    v = warp_min(v);
+    if (threadIdx.x == 0) atomic_min_nonneg(out, v);
+  }
+}
+
+// ---------------------------------------------------------------- advection
+// AdvectionSolverMultiExplicit::MakeIteration for one phase and one stage (advection.hpp:440-480):
+// Superbee face values from Gradient(Interpolate(u)) (solver.hpp:560-619), explicit update.
+template <int DIM>
+DV double adv_face_value(const Geo& g, const double* __restrict__ u, const double* __restrict__ pdinit,
+                         const double* __restrict__ F, int d, int fi, int fj, int fk) {
+  FaceInfo f = face_info<DIM>(g, d, fi, fj, fk);
+  if (f.type == FT_EXCL) return 0.;
+  if (f.type == FT_BOUND) return face_value<DIM, K_PD>(g, u, d, fi, fj, fk, 0, pdinit);
+  const double Ff = F[fidx(g, d, fi, fj, fk)];
+  const double uP = u[f.cm], uE = u[f.cp];
+  const double du = uE - uP;
+  if (Ff > 1e-8) {
+    const double gP = cell_grad<DIM, K_PD>(g, u, d, fi - (d == 0), fj - (d == 1), fk - (d == 2), 0, pdinit);
+    const double pq = -4. * (gP * (-0.5 * g.h[d])) - du;
+    return uP + 0.5 * superbee(du, pq);
+  } else if (Ff < -1e-8) {
+    const double gE = cell_grad<DIM, K_PD>(g, u, d, fi, fj, fk, 0, pdinit);
+    const double pq = 4. * (gE * (0.5 * g.h[d])) - du;
+    return uE - 0.5 * superbee(du, pq);
+  }
+  return 0.5 * (uP + uE);
+}
+template <int DIM>
+__global__ void k_advect(Geo g, const double* __restrict__ u, const double* __restrict__ pdinit,
+                         const double* __restrict__ F, double dt, int num_stages, int stage, double* __restrict__ out) {
+  CELL_LOOP_PROLOG(g)
+  double fsum = 0.;
+#pragma unroll
+  for (int q = 0; q < 2 * DIM; ++q) {
+    if ((q / 2) % num_stages != stage) continue;
+    const int d = q >> 1, o = q & 1;
+    const int fi = i + (d == 0 ? o : 0), fj = j + (d == 1 ? o : 0), fk = k + (d == 2 ? o : 0);
+    const double fu = adv_face_value<DIM>(g, u, pdinit, F, d, fi, fj, fk);
+    fsum += fu * F[fidx(g, d, fi, fj, fk)] * (o ? 1. : -1.);
+  }
+  out[c] = u[c] + -dt / g.vol * fsum;
+}
+
+// ---------------------------------------------------------------- statistics (CalcStat, hydro2d.hpp:1432-1466)
+// out[ph*12 + {0 volume, 1..3 centre sums, 4..6 velocity sums}] (atomicAdd), out[ph*12+7] pd_min, +8 pd_max
+struct StatArgs { int np; const double* vf[3]; const double* pd[3]; const double* u[3]; double* out; };
+template <int DIM>
+__global__ void k_stat(Geo g, StatArgs a) {
+  long long c_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long nc_ = (long long)g.n[0] * g.n[1] * g.n[2];
+  const bool ok = c_ < nc_;
+  int i = 0, j = 0, k = 0;
+  if (ok) { i = (int)(c_ % g.n[0]); j = (int)((c_ / g.n[0]) % g.n[1]); k = (int)(c_ / ((long long)g.n[0] * g.n[1])); }
+  double x[3]; cell_center(g, i, j, k, x);
+  __shared__ double sm[32];
+  for (int ph = 0; ph < a.np; ++ph) {
+    double vals[9];
+    const double cc = ok ? a.vf[ph][c_] : 0.;
+    const double w = cc * g.vol;
+    vals[0] = w;
+    for (int d = 0; d < 3; ++d) { vals[1 + d] = (ok && d < DIM) ? x[d] * w : 0.; vals[4 + d] = (ok && d < DIM) ? a.u[d][c_] * w : 0.; }
+    const double pd = ok ? a.pd[ph][c_] : 0.;
+    vals[7] = ok ? pd : 1e300; vals[8] = ok ? pd : -1e300;
+    for (int q = 0; q < 9; ++q) {
+      double v = vals[q];
+      if (q < 7) v = warp_sum(v); else if (q == 7) v = warp_min(v); else v = warp_max(v);
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        const int nw = blockDim.x >> 5;
+        if (q < 7) { v = threadIdx.x < nw ? sm[threadIdx.x] : 0.; v = warp_sum(v); if (threadIdx.x == 0) atomicAdd(&a.out[ph * 12 + q], v); }
+        else if (q == 7) { v = threadIdx.x < nw ? sm[threadIdx.x] : 1e300; v = warp_min(v);
+          if (threadIdx.x == 0) { // signed doubles: CAS loop
+            unsigned long long* ad = (unsigned long long*)&a.out[ph * 12 + 7]; unsigned long long old = *ad, assumed;
+            do { assumed = old; if (!(v < __longlong_as_double((long long)assumed))) break; old = atomicCAS(ad, assumed, (unsigned long long)__double_as_longlong(v)); } while (assumed != old); } }
+        else { v = threadIdx.x < nw ? sm[threadIdx.x] : -1e300; v = warp_max(v);
+          if (threadIdx.x == 0) {
+            unsigned long long* ad = (unsigned long long*)&a.out[ph * 12 + 8]; unsigned long long old = *ad, assumed;
+            do { assumed = old; if (!(__longlong_as_double((long long)assumed) < v)) break; old = atomicCAS(ad, assumed, (unsigned long long)__double_as_longlong(v)); } while (assumed != old); } }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- initial fields (hydro2d.hpp:310-368, 506-550)
+struct InitArgs {
+  double v0[3]; int pois; int sin_on; double sin_n[3], sin_lambda, sin_phase;
+  double A1[3], B1[3], A2[3], B2[3], IC[3], IR, IC2[3], IR2;
+  int np; double density[3], ivf[3];
+  double* u[3]; double* pd[3];
+};
+DV bool rect_inside(const double* lb, const double* rt, const double* x, int dim) {
+  for (int d = 0; d < dim; ++d) if (x[d] < lb[d] || rt[d] < x[d]) return false;
+  return true;
+}
+template <int DIM>
+__global__ void k_init_fields(Geo g, InitArgs a) {
+  CELL_LOOP_PROLOG(g)
+  double x[3]; cell_center(g, i, j, k, x);
+  double v[3] = {a.v0[0], a.v0[1], DIM > 2 ? a.v0[2] : 0.};
+  if (a.pois) v[0] = x[1] * (1. - x[1]) * 4. * a.v0[0];
+  if (a.sin_on) {
+    const double pi = atan(1.) * 4.;
+    double kd = 0.;
+    for (int d = 0; d < DIM; ++d) kd += (a.sin_n[d] * (2. * pi / a.sin_lambda)) * x[d];
+    const double sn = sin(kd - a.sin_phase);
+    for (int d = 0; d < DIM; ++d) v[d] *= sn;
+  }
+  for (int d = 0; d < DIM; ++d) a.u[d][c] = v[d];
+  double pdv[3];
+  for (int p = 0; p < a.np; ++p) pdv[p] = a.density[p] * a.ivf[p];
+  double d1 = 0., d2 = 0.;
+  for (int d = 0; d < DIM; ++d) { double e = a.IC[d] - x[d]; d1 += e * e; e = a.IC2[d] - x[d]; d2 += e * e; }
+  if (rect_inside(a.A2, a.B2, x, DIM)) { if (a.np > 2) pdv[2] = a.density[2]; }
+  else if (rect_inside(a.A1, a.B1, x, DIM)) { if (a.np > 1) pdv[1] = a.density[1]; }
+  else if (sqrt(d1) < a.IR) { if (a.np > 1) pdv[1] = a.density[1]; }
+  else if (sqrt(d2) < a.IR2) { if (a.np > 1) pdv[1] = a.density[1]; }
+  for (int p = 0; p < a.np; ++p) a.pd[p][c] = pdv[p];
+}
+// partial density of phase 0 compensates the others (hydro2d.hpp:542-550)
+__global__ void k_pd0(int np, double d0, double d1, double d2, const double* pd1, const double* pd2, double* pd0, long long n) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  double vs = 0.;
+  if (np > 1) vs += pd1[c] / d1;
+  if (np > 2) vs += pd2[c] / d2;
+  pd0[c] = (1. - vs) * d0;
+}
+// initial volume flux (FluidSimple ctor, fluid.hpp:770-785): F = Interpolate(u, wall).S - meshvel.S
+template <int DIM>
+__global__ void k_init_flux(Geo g, CP3 u, double mv0, double mv1, double mv2, double* __restrict__ F) {
+  CELL_LOOP_PROLOG(g)
+  (void)c;
+  const double mv[3] = {mv0, mv1, mv2};
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    F[fidx(g, d, i, j, k)] = face_value<DIM, K_VEL>(g, u.p[d], d, i, j, k, d) * g.area[d] - mv[d] * g.area[d];
+    const int x = d == 0 ? i : (d == 1 ? j : k);
+    if (x == g.n[d] - 1) {
+      const int fi = i + (d == 0), fj = j + (d == 1), fk = k + (d == 2);
+      F[fidx(g, d, fi, fj, fk)] = face_value<DIM, K_VEL>(g, u.p[d], d, fi, fj, fk, d) * g.area[d] - mv[d] * g.area[d];
+    }
+  }
+}
+__global__ void k_excl_mask(Geo g, double bx0, double bx1, double bx2, double by0, double by1, double by2,
+                            unsigned char* excl, int* any) {
+  CELL_LOOP_PROLOG(g)
+  double x[3]; cell_center(g, i, j, k, x);
+  const double lb[3] = {bx0, bx1, bx2}, rt[3] = {by0, by1, by2};
+  const bool in = rect_inside(lb, rt, x, g.dim);
+  excl[c] = in ? 1 : 0;
+  if (in) *any = 1;
+}
+__global__ void k_mask_to_double(const unsigned char* m, double* out, long long n) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) out[c] = m ? (m[c] ? 1. : 0.) : 0.;
+}
+// layout conversion natural <-> sheared for the kernel-level linear-solve entry
+template <int DIM>
+__global__ void k_to_sheared(Geo g, const double* __restrict__ in, double* __restrict__ out) {
+  CELL_LOOP_PROLOG(g)
+  out[shidx(g, i, j, k)] = in[c];
+}
+template <int DIM>
+__global__ void k_from_sheared(Geo g, const double* __restrict__ in, double* __restrict__ out) {
+  CELL_LOOP_PROLOG(g)
+  out[c] = in[shidx(g, i, j, k)];
+}

@@ -1,0 +1,992 @@
+// hydro_gpu.cu -- C ABI (include/hydro_gpu.h) over the CUDA kernels: device-resident state of one
+// reference experiment and the orchestration of hydro<Mesh>::step() (hydro2d.hpp:1531-1621).
+// No CPU fallback: every compute entry needs a CUDA device.
+#include "../../include/hydro_gpu.h"
+
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "hg_kernels.cuh"
+#include "hg_solvers.cuh"
+
+enum { L_TC = 0, L_TP = 1, L_IC = 2, L_IP = 3 };
+
+struct Timer { cudaEvent_t a, b; double total = 0.; bool open = false; };
+
+struct hg_state {
+  hg_config cfg;
+  int dev = 0;
+  cudaStream_t st = nullptr;
+  int dim = 0, n[3] = {1, 1, 1};
+  long long nc = 0, nf = 0, nsh = 0;
+  Geo geo;
+  unsigned char* excl = nullptr;
+  bool any_excl = false;
+  double *u[4][3] = {}, *p[4] = {}, *F[4] = {}, *T[4] = {};
+  double* pd[HG_MAX_PHASES][4] = {};
+  double* pd_init[HG_MAX_PHASES] = {};
+  double *vf[HG_MAX_PHASES] = {}, *rho_raw = nullptr, *mu_raw = nullptr, *rho = nullptr, *mu = nullptr, *kc = nullptr;
+  double *force[3] = {}, *stforce[3] = {};
+  double *gp[3] = {}, *fcr[3] = {}, *G[9] = {}, *fs[3] = {}, *dc = nullptr, *Fs = nullptr, *pc = nullptr;
+  double *w1 = nullptr, *w2 = nullptr, *zero = nullptr;
+  double *A[7] = {}, *R[3] = {}, *X[3] = {}, *D = nullptr, *RP = nullptr, *PP = nullptr, *PPsave = nullptr;
+  double* resid = nullptr;    // per-iteration convergence indicators of the current step (device, 4096)
+  double* scal = nullptr;     // device scalars: [0] resid, [1] auto dt, [2..] stat (36), then diffs
+  int* flag = nullptr;        // NaN flag
+  double* hscal = nullptr;    // pinned host mirror
+  int max_sweeps = 0;
+  double* diffs = nullptr;    // per-sweep max norms (device)
+  double* hdiffs = nullptr;   // pinned
+  double time_fluid = 0., time_adv = 0., dt = 0., dt_adv = 0.;
+  double meshpos[3] = {0., 0., 0.};
+  int iter_count = 0;
+  double last_resid = 1.;
+  int sweeps_total = 0; double last_diff = 0.;
+  hg_step_stats stat;
+  long long launches = 0;
+  int grid_solver = 0, grid_lu = 0;
+  bool timers_on = false;
+  std::map<std::string, Timer> timers;
+  std::vector<std::string> timer_stack;
+  std::vector<void*> allocs;
+  std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+#define CK(call)                                                                   \
+  do {                                                                             \
+    cudaError_t e_ = (call);                                                       \
+    if (e_ != cudaSuccess) {                                                       \
+      s->err = std::string(#call) + ": " + cudaGetErrorString(e_);                 \
+      return HG_ERR_CUDA;                                                          \
+    }                                                                              \
+  } while (0)
+
+static inline unsigned nblk(long long n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+template <class T>
+static int dalloc(hg_state* s, T** p, long long n, bool zero = true) {
+  void* q = nullptr;
+  CK(cudaMalloc(&q, (size_t)(n > 0 ? n : 1) * sizeof(T)));
+  if (zero) CK(cudaMemsetAsync(q, 0, (size_t)(n > 0 ? n : 1) * sizeof(T), s->st));
+  s->allocs.push_back(q);
+  *p = (T*)q;
+  return 0;
+}
+
+static void tpush(hg_state* s, const char* name) {
+  if (!s->timers_on) return;
+  Timer& t = s->timers[name];
+  if (!t.a) { cudaEventCreate(&t.a); cudaEventCreate(&t.b); }
+  cudaEventRecord(t.a, s->st);
+  t.open = true;
+  s->timer_stack.push_back(name);
+}
+static void tpop(hg_state* s) {
+  if (!s->timers_on || s->timer_stack.empty()) return;
+  Timer& t = s->timers[s->timer_stack.back()];
+  s->timer_stack.pop_back();
+  cudaEventRecord(t.b, s->st);
+  cudaEventSynchronize(t.b);
+  float ms = 0.f; cudaEventElapsedTime(&ms, t.a, t.b);
+  t.total += ms * 1e-3; t.open = false;
+}
+
+#define LAUNCH(s, kern, grid, block, ...)                      \
+  do { kern<<<grid, block, 0, (s)->st>>>(__VA_ARGS__); ++(s)->launches; } while (0)
+#define DIMSEL(s, KERN, grid, block, ...)                                                     \
+  do { if ((s)->dim == 3) { KERN<3><<<grid, block, 0, (s)->st>>>(__VA_ARGS__); }             \
+       else { KERN<2><<<grid, block, 0, (s)->st>>>(__VA_ARGS__); } ++(s)->launches; } while (0)
+
+static CP3 cp3(double* const a[3]) { CP3 r; for (int d = 0; d < 3; ++d) r.p[d] = a[d]; return r; }
+static P3 p3(double* const a[3]) { P3 r; for (int d = 0; d < 3; ++d) r.p[d] = a[d]; return r; }
+
+// GetDerivativeApproxCoeffs (solver.hpp:816-861), args {-2dt,-dt,0}, target 0
+static void bdf_coeffs(double dt, int second_order, double co[3]) {
+  double args[3] = {-2. * dt, -dt, 0.};
+  int skip = second_order ? 0 : 1, size = 3 - skip;
+  co[0] = co[1] = co[2] = 0.;
+  for (int i = 0; i < size; ++i) {
+    double denom = 1., numer = 0.;
+    for (int j = 0; j < size; ++j) if (j != i) {
+      denom *= args[skip + i] - args[skip + j];
+      double term = 1.;
+      for (int k = 0; k < size; ++k) if (k != i && k != j) term *= 0. - args[skip + k];
+      numer += term;
+    }
+    co[skip + i] = numer / denom;
+  }
+}
+
+// ------------------------------------------------------------------ solvers (host side)
+template <class K, class A>
+static int coop_launch(hg_state* s, K kern, int grid, Geo g, A args) {
+  void* params[] = {(void*)&g, (void*)&args};
+  CK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(SOLVER_THREADS), params, 0, s->st));
+  ++s->launches;
+  return 0;
+}
+
+static int ensure_sweep_capacity(hg_state* s, int nsweeps) {
+  if (nsweeps <= s->max_sweeps) return 0;
+  int cap = nsweeps + 16;
+  CK(cudaMalloc((void**)&s->diffs, cap * sizeof(double)));
+  s->allocs.push_back(s->diffs);
+  CK(cudaMallocHost((void**)&s->hdiffs, cap * sizeof(double)));
+  s->max_sweeps = cap;
+  return 0;
+}
+
+// Runs `do { sweep } while (diff > tol && iter++ < limit)` (linear.hpp:688-710) with pipelined sweeps.
+// launch(s_begin, s_end) must run sweeps [s_begin, s_end) on x; save/restore checkpoint x when a
+// chunk overshoots the stopping sweep.  Returns the reference's `iter` and `diff`.
+template <class LaunchFn>
+static int run_sor(hg_state* s, double* x, long long nx_, double tol, int limit, LaunchFn launch, int* out_iter, double* out_diff) {
+  const int max_total = limit + 1;
+  if (int rc = ensure_sweep_capacity(s, max_total)) return rc;
+  CK(cudaMemsetAsync(x, 0, nx_ * sizeof(double), s->st));
+  CK(cudaMemsetAsync(s->diffs, 0, max_total * sizeof(double), s->st));
+  if (!(tol > 0.)) {
+    // `diff > tol` only fails for diff == 0 (or NaN): run all limit+1 sweeps, inspect the history once
+    if (int rc = launch(0, max_total)) return rc;
+    CK(cudaMemcpyAsync(s->hdiffs, s->diffs, max_total * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    CK(cudaStreamSynchronize(s->st));
+    int stop = -1;
+    for (int k = 0; k < max_total; ++k) if (!(s->hdiffs[k] > tol)) { stop = k; break; }
+    if (stop >= 0 && stop < max_total - 1) {   // stopped early: redo with the exact sweep count
+      const double dstop = s->hdiffs[stop];
+      CK(cudaMemsetAsync(x, 0, nx_ * sizeof(double), s->st));
+      CK(cudaMemsetAsync(s->diffs, 0, max_total * sizeof(double), s->st));
+      if (int rc = launch(0, stop + 1)) return rc;
+      *out_iter = stop; *out_diff = dstop;
+      return 0;
+    }
+    *out_iter = stop >= 0 ? stop : limit + 1;   // `iter++ < limit` increments even when it fails
+    *out_diff = s->hdiffs[max_total - 1];
+    return 0;
+  }
+  int chunk = s->cfg.pressure_sweeps_per_check > 0 ? s->cfg.pressure_sweeps_per_check : 128;
+  int done = 0;
+  while (done < max_total) {
+    int n = std::min(chunk, max_total - done);
+    CK(cudaMemcpyAsync(s->PPsave, x, nx_ * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
+    if (int rc = launch(done, done + n)) return rc;
+    CK(cudaMemcpyAsync(s->hdiffs + done, s->diffs + done, n * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    CK(cudaStreamSynchronize(s->st));
+    int stop = -1;
+    for (int k = done; k < done + n; ++k) if (!(s->hdiffs[k] > tol)) { stop = k; break; }
+    if (stop >= 0) {
+      if (stop != done + n - 1) {
+        CK(cudaMemcpyAsync(x, s->PPsave, nx_ * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
+        if (int rc = launch(done, stop + 1)) return rc;
+      }
+      *out_iter = stop; *out_diff = s->hdiffs[stop];
+      return 0;
+    }
+    done += n;
+  }
+  *out_iter = limit + 1; *out_diff = s->hdiffs[max_total - 1];
+  return 0;
+}
+
+// Jacobi::Solve (linear.hpp:750-782): independent sweeps on the natural layout; the stop test needs the
+// per-sweep norm, fetched every `check` sweeps; the state is recomputed from a checkpoint when the
+// stopping sweep falls inside a batch.  rows == nullptr: pressure rows regenerated from d_c.  Result in s->pc.
+static int run_jacobi(hg_state* s, double* const* rows, const double* D, const double* R, double tol, int limit, double omega,
+                      int* out_iter, double* out_diff) {
+  const int check = 16;
+  if (int rc = ensure_sweep_capacity(s, check + 2)) return rc;
+  double* xc = s->pc; double* xo = s->w2;
+  CK(cudaMemsetAsync(xc, 0, s->nc * sizeof(double), s->st));
+  auto sweeps = [&](int nsw) {
+    double* a_ = xc; double* b_ = xo;
+    for (int q = 0; q < nsw; ++q) {
+      JacArgs a; for (int t = 0; t < 7; ++t) a.A[t] = rows ? rows[t] : nullptr;
+      a.D = D; a.R = R; a.xin = a_; a.xout = b_; a.diff = s->diffs + q; a.omega = omega;
+      DIMSEL(s, k_jacobi_sweep, nblk(s->nc), 256, s->geo, a);
+      std::swap(a_, b_);
+    }
+  };
+  int done = 0;
+  for (;;) {
+    const int nb = std::min(check, limit + 1 - done);
+    CK(cudaMemcpyAsync(s->PPsave, xc, s->nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
+    CK(cudaMemsetAsync(s->diffs, 0, nb * sizeof(double), s->st));
+    sweeps(nb);
+    CK(cudaMemcpyAsync(s->hdiffs, s->diffs, nb * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    CK(cudaStreamSynchronize(s->st));
+    int nsw = -1;
+    for (int q = 0; q < nb; ++q) {
+      const int k = done + q;
+      if (!(s->hdiffs[q] > tol)) { *out_iter = k; *out_diff = s->hdiffs[q]; nsw = q + 1; break; }
+      if (!(k < limit)) { *out_iter = k + 1; *out_diff = s->hdiffs[q]; nsw = q + 1; break; }
+    }
+    if (nsw < 0) { done += nb; if (nb & 1) std::swap(xc, xo); continue; }
+    if (nsw != nb) {
+      CK(cudaMemcpyAsync(xc, s->PPsave, s->nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
+      CK(cudaMemsetAsync(s->diffs, 0, nb * sizeof(double), s->st));
+      sweeps(nsw);
+    }
+    if (nsw & 1) std::swap(xc, xo);
+    break;
+  }
+  if (xc != s->pc) CK(cudaMemcpyAsync(s->pc, xc, s->nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
+  return 0;
+}
+
+static int solve_pressure(hg_state* s) {
+  const hg_config& c = s->cfg;
+  int it = 0; double df = 0.;
+  if (c.linear_solver_pressure == HG_LS_GAUSS_SEIDEL) {
+    auto launch = [&](int sb, int se) -> int {
+      GsArgs a; a.D = s->D; a.RP = s->RP; a.PP = s->PP; a.diff = s->diffs; a.s_begin = sb; a.s_end = se;
+      a.omega = c.lu_relaxed_relaxation_factor;
+      if (s->dim == 3) return coop_launch(s, k_gs_persistent<3>, s->grid_solver, s->geo, a);
+      return coop_launch(s, k_gs_persistent<2>, s->grid_solver, s->geo, a);
+    };
+    if (int rc = run_sor(s, s->PP, s->nsh, c.lu_relaxed_tolerance, c.lu_relaxed_num_iters_limit, launch, &it, &df)) return rc;
+    DIMSEL(s, k_pcorr, nblk(s->nc), 256, s->geo, s->PP, s->p[L_IP], c.pressure_relaxation_factor, s->pc, s->p[L_IC]);
+  } else if (c.linear_solver_pressure == HG_LS_JACOBI) {
+    // natural layout: constants back from the sheared array, rows regenerated from d_c
+    DIMSEL(s, k_from_sheared, nblk(s->nc), 256, s->geo, s->RP, s->w1);
+    if (int rc = run_jacobi(s, nullptr, s->dc, s->w1, c.lu_relaxed_tolerance, c.lu_relaxed_num_iters_limit,
+                            c.lu_relaxed_relaxation_factor, &it, &df)) return rc;
+    // p_curr = p_prev + alpha p'
+    DIMSEL(s, k_to_sheared, nblk(s->nc), 256, s->geo, s->pc, s->PP);
+    DIMSEL(s, k_pcorr, nblk(s->nc), 256, s->geo, s->PP, s->p[L_IP], c.pressure_relaxation_factor, s->pc, s->p[L_IC]);
+  } else {
+    s->err = "linear_solver_pressure: only gauss_seidel and jacobi run on the GPU path";
+    return HG_ERR_INVALID;
+  }
+  s->sweeps_total += it + 1; s->last_diff = df;
+  return 0;
+}
+
+static int solve_lu(hg_state* s, int ncomp) {
+  LuArgs a;
+  for (int t = 0; t < 7; ++t) a.A[t] = s->A[t];
+  for (int n = 0; n < 3; ++n) { a.R[n] = s->R[n]; a.X[n] = s->X[n]; }
+  a.ncomp = ncomp;
+  if (s->dim == 3) return coop_launch(s, k_lu_persistent<3>, s->grid_lu, s->geo, a);
+  return coop_launch(s, k_lu_persistent<2>, s->grid_lu, s->geo, a);
+}
+
+// ------------------------------------------------------------------ properties / statistics
+static int smooth_field(hg_state* s, const double* in, int repeat, double* out) {
+  // GetSmoothField (solver.hpp:636-656); ping-pong between out and w2
+  if (repeat <= 0) { if (in != out) CK(cudaMemcpyAsync(out, in, s->nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st)); return 0; }
+  const double* src = in;
+  double* bufs[2] = {(repeat % 2) ? out : s->w2, (repeat % 2) ? s->w2 : out};
+  for (int r = 0; r < repeat; ++r) {
+    double* dst = bufs[r % 2];
+    DIMSEL(s, k_smooth, nblk(s->nc), 256, s->geo, src, dst);
+    src = dst;
+  }
+  return 0;
+}
+
+extern "C" int hg_update_properties(hg_handle s) {
+  if (!s) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  tpush(s, "step.fluid_properties");
+  const hg_config& c = s->cfg;
+  PropArgs a; a.np = c.num_phases;
+  for (int p = 0; p < 3; ++p) {
+    a.density[p] = c.density[p]; a.viscosity[p] = c.viscosity[p]; a.conductivity[p] = c.conductivity[p];
+    a.pd[p] = s->pd[p][L_TC]; a.vf[p] = s->vf[p];
+  }
+  a.rho_raw = s->rho_raw; a.mu_raw = s->mu_raw; a.kc = s->kc;
+  LAUNCH(s, k_volfrac, nblk(s->nc), 256, a, s->nc);
+  if (int rc = smooth_field(s, s->rho_raw, c.density_smooth_times, s->rho)) return rc;
+  if (int rc = smooth_field(s, s->mu_raw, c.viscosity_smooth_times, s->mu)) return rc;
+  LAUNCH(s, k_force, nblk(s->nc), 256, s->dim, s->rho_raw, c.gravity[0], c.gravity[1], c.gravity[2], c.force[0], c.force[1],
+         c.force[2], p3(s->force), s->nc);
+  if (c.num_phases >= 2 && c.sigma != 0.) {
+    P3 gs; for (int d = 0; d < 3; ++d) gs.p[d] = s->G[d];
+    DIMSEL(s, k_grad_pd, nblk(s->nc), 256, s->geo, s->vf[1], s->pd_init[0], gs);
+    CP3 gsc; for (int d = 0; d < 3; ++d) gsc.p[d] = s->G[d];
+    DIMSEL(s, k_stforce, nblk(s->nc), 256, s->geo, gsc, c.sigma, p3(s->stforce));
+  }
+  if (c.force_smooth_times > 0) {
+    for (int d = 0; d < s->dim; ++d) {
+      if (int rc = smooth_field(s, s->force[d], c.force_smooth_times, s->w1)) return rc;
+      CK(cudaMemcpyAsync(s->force[d], s->w1, s->nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
+    }
+  }
+  tpop(s);
+  return 0;
+}
+
+extern "C" int hg_calc_stat(hg_handle s, hg_step_stats* st) {
+  if (!s) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  const hg_config& c = s->cfg;
+  double init[36];
+  for (int p = 0; p < 3; ++p) { for (int q = 0; q < 12; ++q) init[p * 12 + q] = 0.; init[p * 12 + 7] = 1e10; init[p * 12 + 8] = -1e10; }
+  CK(cudaMemcpyAsync(s->scal + 2, init, sizeof(init), cudaMemcpyHostToDevice, s->st));
+  StatArgs a; a.np = c.num_phases;
+  for (int p = 0; p < 3; ++p) { a.vf[p] = s->vf[p]; a.pd[p] = s->pd[p][L_TC]; }
+  for (int d = 0; d < 3; ++d) a.u[d] = s->u[L_TC][d] ? s->u[L_TC][d] : s->zero;
+  a.out = s->scal + 2;
+  DIMSEL(s, k_stat, nblk(s->nc), 256, s->geo, a);
+  CK(cudaMemcpyAsync(s->hscal + 2, s->scal + 2, 36 * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+  CK(cudaStreamSynchronize(s->st));
+  hg_step_stats& o = s->stat;
+  for (int p = 0; p < c.num_phases; ++p) {
+    const double* r = s->hscal + 2 + p * 12;
+    o.volume[p] = r[0]; o.mass[p] = r[0] * c.density[p]; o.pd_min[p] = r[7]; o.pd_max[p] = r[8];
+    for (int d = 0; d < 3; ++d) {
+      o.center[p][d] = d < s->dim ? r[1 + d] / r[0] + s->meshpos[d] : 0.;
+      o.velocity[p][d] = d < s->dim ? r[4 + d] / r[0] : 0.;
+    }
+  }
+  if (c.meshvel_output) for (int d = 0; d < s->dim; ++d) s->meshpos[d] += c.meshvel[d] * s->dt;
+  if (st) {
+    for (int p = 0; p < HG_MAX_PHASES; ++p) {
+      st->volume[p] = o.volume[p]; st->mass[p] = o.mass[p]; st->pd_min[p] = o.pd_min[p]; st->pd_max[p] = o.pd_max[p];
+      for (int d = 0; d < 3; ++d) { st->center[p][d] = o.center[p][d]; st->velocity[p][d] = o.velocity[p][d]; }
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ fluid solver protocol
+static int check_nan(hg_state* s, const double* a, long long n, const char* msg) {
+  CK(cudaMemsetAsync(s->flag, 0, sizeof(int), s->st));
+  LAUNCH(s, k_nan_flag, nblk(n), 256, a, n, s->flag);
+  int h = 0;
+  CK(cudaMemcpyAsync(&h, s->flag, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+  CK(cudaStreamSynchronize(s->st));
+  if (h) { s->err = msg; return HG_ERR_NAN; }
+  return 0;
+}
+
+extern "C" int hg_fluid_start_step(hg_handle s) {   // fluid.hpp:793-812
+  if (!s) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  s->iter_count = 0;
+  CK(cudaMemsetAsync(s->resid, 0, 4096 * sizeof(double), s->st));
+  if (int rc = check_nan(s, s->p[L_TC], s->nc, "NaN initial pressure")) return rc;
+  const double ge = s->cfg.guess_extrapolation;
+  for (int d = 0; d < s->dim; ++d) {
+    if (int rc = check_nan(s, s->u[L_TC][d], s->nc, "NaN initial field")) return rc;
+    LAUNCH(s, k_start_layer, nblk(s->nc), 256, s->u[L_IC][d], s->u[L_TC][d], s->u[L_TP][d], ge, s->nc);
+  }
+  LAUNCH(s, k_start_layer, nblk(s->nc), 256, s->p[L_IC], s->p[L_TC], s->p[L_TP], ge, s->nc);
+  LAUNCH(s, k_start_layer, nblk(s->nf), 256, s->F[L_IC], s->F[L_TC], s->F[L_TP], ge, s->nf);
+  return 0;
+}
+
+extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
+  if (!s) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  const hg_config& c = s->cfg;
+  const unsigned gb = nblk(s->nc);
+  // iter_prev <- iter_curr by pointer rotation: every kernel below writes all of the new iter_curr
+  std::swap(s->p[L_IP], s->p[L_IC]);
+  std::swap(s->F[L_IP], s->F[L_IC]);
+  for (int d = 0; d < s->dim; ++d) std::swap(s->u[L_IP][d], s->u[L_IC][d]);
+  // from here on: *_IP hold the state the iteration starts from
+
+  tpush(s, "fluid.0.pressure-gradient");
+  DIMSEL(s, k_pre, gb, 256, s->geo, cp3(s->force), s->p[L_IP], p3(s->fcr), p3(s->gp));
+  tpop(s);
+  tpush(s, "fluid.1a.explicit-viscosity");
+  { P9 G; for (int q = 0; q < 9; ++q) G.p[q] = s->G[q];
+    DIMSEL(s, k_velgrad, gb, 256, s->geo, cp3(s->u[L_IP]), G);
+    P9c Gc; for (int q = 0; q < 9; ++q) Gc.p[q] = s->G[q];
+    const int use_stf = (c.num_phases >= 2 && c.sigma != 0.) ? 1 : 0;
+    DIMSEL(s, k_source, gb, 256, s->geo, Gc, s->mu, cp3(s->gp), cp3(s->fcr), cp3(s->stforce), use_stf, p3(s->fs)); }
+  tpop(s);
+  tpush(s, "fluid.2.convection-diffusion");
+  { AsmArgs a;
+    for (int n = 0; n < 3; ++n) { a.prev[n] = s->u[L_IP][n]; a.tc[n] = s->u[L_TC][n]; a.tp[n] = s->u[L_TP][n]; a.src[n] = s->fs[n]; a.R[n] = s->R[n]; }
+    for (int q = 0; q < 9; ++q) a.grad[q] = s->G[q];
+    a.rho = s->rho; a.mu = s->mu; a.F = s->F[L_IP];
+    bdf_coeffs(s->dt, c.time_second_order, a.co);
+    a.relax = c.velocity_relaxation_factor;
+    for (int t = 0; t < 7; ++t) a.A[t] = s->A[t];
+    a.coeffsum = s->dc; a.coeffsum_div = (double)s->dim;
+    if (s->dim == 3) { k_assemble<3, K_VEL, 3><<<gb, 256, 0, s->st>>>(s->geo, a); }
+    else { k_assemble<2, K_VEL, 2><<<gb, 256, 0, s->st>>>(s->geo, a); }
+    ++s->launches;
+    if (c.linear_solver_velocity != HG_LS_LU) { s->err = "linear_solver_velocity: only lu runs on the GPU path"; return HG_ERR_INVALID; }
+    if (int rc = solve_lu(s, s->dim)) return rc;
+    if (s->dim == 3) { k_apply_corr<3, 3><<<gb, 256, 0, s->st>>>(s->geo, cp3(s->u[L_IP]), cp3(s->X), p3(s->u[L_IC])); }
+    else { k_apply_corr<2, 2><<<gb, 256, 0, s->st>>>(s->geo, cp3(s->u[L_IP]), cp3(s->X), p3(s->u[L_IC])); }
+    ++s->launches; }
+  tpop(s);
+  tpush(s, "fluid.3.momentum-interpolation");
+  { FstarArgs a;
+    for (int d = 0; d < 3; ++d) { a.us[d] = s->u[L_IC][d]; a.gp[d] = s->gp[d]; a.fcr[d] = s->fcr[d]; a.force[d] = s->force[d]; a.meshvel[d] = c.meshvel[d]; }
+    a.pprev = s->p[L_IP]; a.dc = s->dc; a.rc = c.rhie_chow_factor; a.Fs = s->Fs;
+    DIMSEL(s, k_fstar, gb, 256, s->geo, a); }
+  tpop(s);
+  tpush(s, "fluid.5.pressure-system");
+  DIMSEL(s, k_prhs, gb, 256, s->geo, s->Fs, s->dc, s->RP, s->D);
+  tpop(s);
+  tpush(s, "fluid.6.pressure-solve");
+  if (int rc = solve_pressure(s)) return rc;
+  tpop(s);
+  tpush(s, "fluid.7.correction");
+  { CorrArgs a; a.pc = s->pc; a.dc = s->dc; a.Fs = s->Fs; a.F = s->F[L_IC];
+    for (int d = 0; d < 3; ++d) a.u[d] = s->u[L_IC][d];
+    DIMSEL(s, k_correct, gb, 256, s->geo, a); }
+  tpop(s);
+  // convergence indicator (fluid.hpp:174-179): computed now into resid[iteration], fetched lazily
+  double* rdst = s->resid + (s->iter_count < 4096 ? s->iter_count : 4095);
+  if (s->iter_count >= 4095) CK(cudaMemsetAsync(rdst, 0, sizeof(double), s->st));
+  if (s->dim == 3) { k_resid<3><<<gb, 256, 0, s->st>>>(cp3(s->u[L_IC]), cp3(s->u[L_IP]), s->nc, rdst); }
+  else { k_resid<2><<<gb, 256, 0, s->st>>>(cp3(s->u[L_IC]), cp3(s->u[L_IP]), s->nc, rdst); }
+  ++s->launches;
+  ++s->iter_count;
+  s->last_resid = -1.;   // not fetched yet
+  return 0;
+}
+
+extern "C" int hg_fluid_convergence_indicator(hg_handle s, double* out) {
+  if (!s || !out) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  if (s->iter_count == 0) { *out = 1.; return 0; }
+  if (s->last_resid < 0.) {
+    const int idx = s->iter_count - 1 < 4095 ? s->iter_count - 1 : 4095;
+    CK(cudaMemcpyAsync(s->hscal, s->resid + idx, sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    CK(cudaStreamSynchronize(s->st));
+    s->last_resid = s->hscal[0];
+  }
+  *out = s->last_resid;
+  return 0;
+}
+
+extern "C" int hg_fluid_is_converged(hg_handle s, int* out) {   // solver.hpp:733-736
+  if (!s || !out) return HG_ERR_INVALID;
+  if (s->iter_count >= s->cfg.num_iterations_limit) { *out = 1; return 0; }
+  if (!(s->cfg.convergence_tolerance > 0.)) { *out = 0; return 0; }   // indicator >= 0 is never < tol
+  double r; if (int rc = hg_fluid_convergence_indicator(s, &r)) return rc;
+  *out = r < s->cfg.convergence_tolerance;
+  return 0;
+}
+
+extern "C" int hg_fluid_finish_step(hg_handle s) {   // fluid.hpp:1159-1169, conv_diff.hpp:252-259
+  if (!s) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  // time_prev <- time_curr, time_curr <- iter_curr: rotate buffers, iter_curr keeps the old time_prev storage
+  auto rot = [](double*& tc, double*& tp, double*& ic) { double* o = tp; tp = tc; tc = ic; ic = o; };
+  rot(s->p[L_TC], s->p[L_TP], s->p[L_IC]);
+  rot(s->F[L_TC], s->F[L_TP], s->F[L_IC]);
+  for (int d = 0; d < s->dim; ++d) rot(s->u[L_TC][d], s->u[L_TP][d], s->u[L_IC][d]);
+  if (int rc = check_nan(s, s->p[L_TC], s->nc, "NaN pressure")) return rc;
+  for (int d = 0; d < s->dim; ++d) if (int rc = check_nan(s, s->u[L_TC][d], s->nc, "NaN field")) return rc;
+  s->time_fluid += s->dt;
+  return 0;
+}
+
+extern "C" int hg_fluid_auto_time_step(hg_handle s, double* out) {
+  if (!s || !out) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  double init = 1e10;
+  CK(cudaMemcpyAsync(s->scal + 1, &init, sizeof(double), cudaMemcpyHostToDevice, s->st));
+  DIMSEL(s, k_auto_dt, nblk(s->nc), 256, s->geo, s->F[L_TC], s->scal + 1);
+  CK(cudaMemcpyAsync(s->hscal + 1, s->scal + 1, sizeof(double), cudaMemcpyDeviceToHost, s->st));
+  CK(cudaStreamSynchronize(s->st));
+  *out = s->hscal[1];
+  return 0;
+}
+
+extern "C" int hg_set_time_step(hg_handle s, double dt_fluid, double dt_adv) {
+  if (!s) return HG_ERR_INVALID;
+  s->dt = dt_fluid; s->dt_adv = dt_adv;
+  return 0;
+}
+
+extern "C" int hg_advection_step(hg_handle s) {   // advection.hpp:417-545
+  if (!s) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  const hg_config& c = s->cfg;
+  const int num_stages = c.tvd_split ? s->dim : 1;
+  for (int ph = 0; ph < c.num_phases; ++ph) {
+    // StartStep: time_prev = time_curr (values); the update reads time_curr and writes a fresh buffer
+    double* src = s->pd[ph][L_TC];
+    CK(cudaMemcpyAsync(s->pd[ph][L_TP], src, s->nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
+    double* bufs[2] = {s->pd[ph][L_IC], s->pd[ph][L_IP]};
+    const double* in = src;
+    double* out = nullptr;
+    for (int stage = 0; stage < num_stages; ++stage) {
+      out = bufs[stage % 2];
+      DIMSEL(s, k_advect, nblk(s->nc), 256, s->geo, in, s->pd_init[ph], s->F[L_TC], s->dt_adv, num_stages, stage, out);
+      in = out;
+    }
+    // FinishStep: time_curr = iter_curr
+    if (out == s->pd[ph][L_IC]) std::swap(s->pd[ph][L_TC], s->pd[ph][L_IC]);
+    else std::swap(s->pd[ph][L_TC], s->pd[ph][L_IP]);
+  }
+  s->time_adv += s->dt_adv;
+  return 0;
+}
+
+extern "C" int hg_heat_step(hg_handle s) {   // heat.hpp:69-84 + conv_diff.hpp:118-259, one iteration
+  if (!s) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  const hg_config& c = s->cfg;
+  if (c.linear_solver_heat != HG_LS_LU) { s->err = "linear_solver_heat: only lu runs on the GPU path"; return HG_ERR_INVALID; }
+  if (int rc = check_nan(s, s->T[L_TC], s->nc, "NaN initial field")) return rc;
+  const unsigned gb = nblk(s->nc);
+  // gradient of the temperature for the deferred upwind correction (conv_diff.hpp:135)
+  P3 g3; for (int d = 0; d < 3; ++d) g3.p[d] = s->G[d];
+  if (s->dim == 3) { k_interp_grad<3, K_TEMP><<<gb, 256, 0, s->st>>>(s->geo, s->T[L_TC], 0, g3); }
+  else { k_interp_grad<2, K_TEMP><<<gb, 256, 0, s->st>>>(s->geo, s->T[L_TC], 0, g3); }
+  ++s->launches;
+  AsmArgs a;
+  for (int n = 0; n < 3; ++n) { a.prev[n] = s->T[L_TC]; a.tc[n] = s->T[L_TC]; a.tp[n] = s->T[L_TP]; a.src[n] = s->zero; a.R[n] = s->R[n]; }
+  for (int q = 0; q < 9; ++q) a.grad[q] = s->G[q % 3];
+  a.rho = nullptr; a.mu = s->kc; a.F = s->F[L_TC];
+  bdf_coeffs(c.dt /* HeatSolver keeps the time step of its constructor (hydro2d.hpp:684) */, c.time_second_order_heat, a.co);
+  a.relax = c.heat_relaxation_factor;
+  for (int t = 0; t < 7; ++t) a.A[t] = s->A[t];
+  a.coeffsum = nullptr; a.coeffsum_div = 1.;
+  if (s->dim == 3) { k_assemble<3, K_TEMP, 1><<<gb, 256, 0, s->st>>>(s->geo, a); }
+  else { k_assemble<2, K_TEMP, 1><<<gb, 256, 0, s->st>>>(s->geo, a); }
+  ++s->launches;
+  if (int rc = solve_lu(s, 1)) return rc;
+  CP3 prev, X; P3 curr;
+  for (int d = 0; d < 3; ++d) { prev.p[d] = s->T[L_TC]; X.p[d] = s->X[d]; curr.p[d] = s->T[L_IC]; }
+  if (s->dim == 3) { k_apply_corr<3, 1><<<gb, 256, 0, s->st>>>(s->geo, prev, X, curr); }
+  else { k_apply_corr<2, 1><<<gb, 256, 0, s->st>>>(s->geo, prev, X, curr); }
+  ++s->launches;
+  // FinishStep: time_prev <- time_curr <- iter_curr
+  double* o = s->T[L_TP]; s->T[L_TP] = s->T[L_TC]; s->T[L_TC] = s->T[L_IC]; s->T[L_IC] = o;
+  if (int rc = check_nan(s, s->T[L_TC], s->nc, "NaN field")) return rc;
+  return 0;
+}
+
+extern "C" int hg_step(hg_handle s, hg_step_stats* stats) {   // hydro2d.hpp:1531-1621
+  if (!s) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  const hg_config& c = s->cfg;
+  int rc;
+  tpush(s, "step");
+  s->sweeps_total = 0;
+  if (c.dt_auto) {
+    double dtm; if ((rc = hg_fluid_auto_time_step(s, &dtm))) return rc;
+    s->dt = dtm * c.cfl; s->dt_adv = dtm * c.cfl_advection;
+  }
+  tpush(s, "step.fluid");
+  if ((rc = hg_fluid_start_step(s))) return rc;
+  if (c.fluid_enable) {
+    int conv; if ((rc = hg_fluid_is_converged(s, &conv))) return rc;
+    while (!conv) {
+      if ((rc = hg_fluid_make_iteration(s))) return rc;
+      if ((rc = hg_fluid_is_converged(s, &conv))) return rc;
+    }
+  }
+  if ((rc = hg_fluid_finish_step(s))) return rc;
+  tpop(s);
+  int nadv = 0;
+  if (c.advection_enable) {
+    tpush(s, "step.advection");
+    while (s->time_adv < s->time_fluid - 0.5 * s->dt_adv) { if ((rc = hg_advection_step(s))) return rc; ++nadv; }
+    tpop(s);
+  }
+  if (c.heat_enable) { tpush(s, "step.heat"); if ((rc = hg_heat_step(s))) return rc; tpop(s); }
+  if ((rc = hg_update_properties(s))) return rc;
+  if ((rc = hg_calc_stat(s, nullptr))) return rc;
+  tpop(s);
+  s->stat.simple_iterations = s->iter_count;
+  double r = 1.; if (s->iter_count > 0) hg_fluid_convergence_indicator(s, &r);
+  s->stat.convergence_indicator = r;
+  s->stat.pressure_sweeps_total = s->sweeps_total;
+  s->stat.pressure_last_diff = s->last_diff;
+  s->stat.advection_substeps = nadv;
+  s->stat.dt = s->dt; s->stat.time = s->time_fluid;
+  if (stats) *stats = s->stat;
+  return 0;
+}
+
+extern "C" int hg_run(hg_handle s, int nsteps, hg_step_stats* last) {
+  for (int i = 0; i < nsteps; ++i) if (int rc = hg_step(s, i == nsteps - 1 ? last : nullptr)) return rc;
+  return 0;
+}
+
+// ------------------------------------------------------------------ lifetime
+extern "C" void hg_config_defaults(hg_config* c) {   // examples/general.hydroconf
+  memset(c, 0, sizeof *c);
+  c->dim = 2; c->Nx = 100; c->Ny = 100; c->Nz = 5;
+  c->B[0] = c->B[1] = c->B[2] = 1.;
+  c->B1[2] = 1.; c->B2[2] = 1.;
+  c->dt = 0.01; c->cfl = 0.5; c->cfl_advection = 0.5;
+  c->num_phases = 1;
+  for (int i = 0; i < HG_MAX_PHASES; ++i) { c->density[i] = 1.; c->viscosity[i] = 1.; c->conductivity[i] = 1.; }
+  c->fluid_enable = 1; c->advection_enable = 1;
+  c->advection_dt_factor = 0.1;
+  c->convergence_tolerance = 1e-2; c->num_iterations_limit = 10;
+  c->velocity_relaxation_factor = 0.8; c->pressure_relaxation_factor = 0.9;
+  c->linear_solver_velocity = HG_LS_LU; c->linear_solver_pressure = HG_LS_GAUSS_SEIDEL; c->linear_solver_heat = HG_LS_LU;
+  c->lu_relaxed_relaxation_factor = 1.9; c->lu_relaxed_num_iters_limit = 1000; c->lu_relaxed_tolerance = 1e-3;
+  c->time_second_order = 1; c->rhie_chow_factor = 1.;
+  c->initial_volume_fraction_smooth_times = 2; c->density_smooth_times = 2; c->viscosity_smooth_times = 2;
+  c->heat_relaxation_factor = 1.; c->time_second_order_heat = 1; c->meshvel_output = 1;
+  c->world_size = 1;
+}
+
+static int fail_create(hg_state* s, int code, const std::string& msg) {
+  g_create_err = msg;
+  if (s) {
+    for (void* p : s->allocs) cudaFree(p);
+    if (s->hscal) cudaFreeHost(s->hscal);
+    if (s->hdiffs) cudaFreeHost(s->hdiffs);
+    if (s->st) cudaStreamDestroy(s->st);
+    delete s;
+  }
+  return code;
+}
+
+extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
+  if (!cfg || !out) { g_create_err = "null argument"; return HG_ERR_INVALID; }
+  *out = nullptr;
+  if ((cfg->dim != 2 && cfg->dim != 3) || cfg->Nx < 1 || cfg->Ny < 1 || (cfg->dim == 3 && cfg->Nz < 1))
+    return fail_create(nullptr, HG_ERR_INVALID, "bad mesh size / dim");
+  if (cfg->num_phases < 1 || cfg->num_phases > HG_MAX_PHASES) return fail_create(nullptr, HG_ERR_INVALID, "num_phases must be 1..3");
+  if (cfg->simpler) return fail_create(nullptr, HG_ERR_INVALID, "simpler 1 is not on the GPU path");
+  if (cfg->force_geometric_average) return fail_create(nullptr, HG_ERR_INVALID, "force_geometric_average 1 is not on the GPU path");
+  if (cfg->sharp != 0.) return fail_create(nullptr, HG_ERR_INVALID, "sharp != 0 is not on the GPU path");
+  for (int sd = 0; sd < 2 * cfg->dim; ++sd)
+    if (cfg->condition_kind[sd] == HG_BC_OUTLET) return fail_create(nullptr, HG_ERR_INVALID, "outlet conditions are not on the GPU path");
+  if (cfg->world_size > 1) return fail_create(nullptr, HG_ERR_INVALID, "world_size > 1: use the slab driver (hydro_b200.parallel)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail_create(nullptr, HG_ERR_NO_DEVICE, "no CUDA device: the GPU path has no CPU fallback");
+  hg_state* s = new hg_state();
+  s->cfg = *cfg;
+  s->dev = cfg->device;
+  if (s->dev < 0 || s->dev >= ndev) return fail_create(s, HG_ERR_INVALID, "bad device index");
+  if (cudaSetDevice(s->dev) != cudaSuccess) return fail_create(s, HG_ERR_CUDA, "cudaSetDevice failed");
+  int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s->dev);
+  if (!coop) return fail_create(s, HG_ERR_CUDA, "device lacks cooperative launch");
+  if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess) return fail_create(s, HG_ERR_CUDA, "stream create failed");
+  const int dim = s->dim = cfg->dim;
+  s->n[0] = cfg->Nx; s->n[1] = cfg->Ny; s->n[2] = dim > 2 ? cfg->Nz : 1;
+  s->nc = (long long)s->n[0] * s->n[1] * s->n[2];
+  Geo& g = s->geo;
+  memset(&g, 0, sizeof g);
+  g.dim = dim; g.sy = s->n[0]; g.sz = (long long)s->n[0] * s->n[1];
+  g.vol = 1.;
+  for (int d = 0; d < 3; ++d) {
+    g.n[d] = s->n[d]; g.lb[d] = cfg->A[d];
+    g.h[d] = d < dim ? (cfg->B[d] - cfg->A[d]) / s->n[d] : 1.;
+    if (d < dim) g.vol *= g.h[d];
+  }
+  for (int d = 0; d < 3; ++d) { g.area[d] = 1.; if (d < dim) for (int e = 0; e < dim; ++e) if (e != d) g.area[d] *= g.h[e]; }
+  s->nf = 0;
+  for (int d = 0; d < 3; ++d) {
+    g.foff[d] = s->nf;
+    if (d < dim) s->nf += (long long)(s->n[0] + (d == 0)) * (s->n[1] + (d == 1)) * (s->n[2] + (d == 2));
+  }
+  g.np = s->n[0] + s->n[1] + s->n[2] - 2;
+  s->nsh = (long long)g.np * s->n[1] * s->n[0];
+  for (int sd = 0; sd < 6; ++sd) { g.bckind[sd] = cfg->condition_kind[sd]; for (int d = 0; d < 3; ++d) g.bcvel[sd][d] = cfg->condition_velocity[sd][d]; }
+  g.bckind[6] = HG_BC_WALL;
+  for (int d = 0; d < 3; ++d) { g.heat_lb[d] = cfg->heat_box_lb[d]; g.heat_rt[d] = cfg->heat_box_rt[d]; }
+  g.heat_T = cfg->heat_box_temperature;
+  g.pfix = -1; g.pfix_value = cfg->pressure_fixed_value;
+  g.excl = nullptr;
+
+  hg_state* sck = s;
+  auto A_ = [&](double** p, long long n) -> bool { return dalloc(sck, p, n) == 0; };
+  bool ok = true;
+  const long long nc = s->nc, nf = s->nf;
+  for (int l = 0; l < 4 && ok; ++l) {
+    for (int d = 0; d < dim && ok; ++d) ok = A_(&s->u[l][d], nc);
+    ok = ok && A_(&s->p[l], nc) && A_(&s->F[l], nf);
+    if (cfg->heat_enable && l < 3) ok = ok && A_(&s->T[l], nc);
+    for (int ph = 0; ph < cfg->num_phases && ok; ++ph) ok = A_(&s->pd[ph][l], nc);
+  }
+  for (int ph = 0; ph < cfg->num_phases && ok; ++ph) ok = A_(&s->vf[ph], nc) && A_(&s->pd_init[ph], nc);
+  ok = ok && A_(&s->rho_raw, nc) && A_(&s->mu_raw, nc) && A_(&s->rho, nc) && A_(&s->mu, nc) && A_(&s->kc, nc);
+  ok = ok && A_(&s->dc, nc) && A_(&s->Fs, nf) && A_(&s->pc, nc) && A_(&s->w1, nc) && A_(&s->w2, nc) && A_(&s->zero, nc);
+  for (int d = 0; d < dim && ok; ++d) ok = A_(&s->force[d], nc) && A_(&s->stforce[d], nc) && A_(&s->gp[d], nc) && A_(&s->fcr[d], nc) && A_(&s->fs[d], nc);
+  for (int q = 0; q < dim * dim && ok; ++q) ok = A_(&s->G[q], nc);
+  for (int t = 0; t < 7 && ok; ++t) ok = A_(&s->A[t], s->nsh);
+  for (int n = 0; n < dim && ok; ++n) ok = A_(&s->R[n], s->nsh) && A_(&s->X[n], s->nsh);
+  ok = ok && A_(&s->D, s->nsh) && A_(&s->RP, s->nsh) && A_(&s->PP, s->nsh) && A_(&s->PPsave, s->nsh);
+  ok = ok && A_(&s->scal, 64) && A_(&s->resid, 4096);
+  if (ok) { int* fp = nullptr; ok = dalloc(s, &fp, 4) == 0; s->flag = fp; }
+  if (ok) { unsigned char* ep = nullptr; ok = dalloc(s, &ep, nc) == 0; s->excl = ep; }
+  if (!ok || cudaMallocHost((void**)&s->hscal, 64 * sizeof(double)) != cudaSuccess) return fail_create(s, HG_ERR_CUDA, "allocation failed: " + s->err);
+  // unused component slots alias a zero array so structs of 3 pointers are always valid
+  for (int d = dim; d < 3; ++d) {
+    for (int l = 0; l < 4; ++l) s->u[l][d] = nullptr;
+    s->force[d] = s->stforce[d] = s->gp[d] = s->fcr[d] = s->fs[d] = s->zero;
+    s->R[d] = s->X[d] = s->PPsave;
+  }
+  for (int q = dim * dim; q < 9; ++q) s->G[q] = s->zero;
+
+  // solver grids: persistent cooperative kernels, all CTAs co-resident
+  cudaDeviceProp prop; cudaGetDeviceProperties(&prop, s->dev);
+  int occ_gs = 0, occ_lu = 0;
+  if (dim == 3) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gs, k_gs_persistent<3>, SOLVER_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lu, k_lu_persistent<3>, SOLVER_THREADS, 0);
+  } else {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gs, k_gs_persistent<2>, SOLVER_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lu, k_lu_persistent<2>, SOLVER_THREADS, 0);
+  }
+  if (occ_gs < 1 || occ_lu < 1) return fail_create(s, HG_ERR_CUDA, "solver kernel does not fit on an SM");
+  s->grid_solver = prop.multiProcessorCount * std::min(occ_gs, 4);
+  s->grid_lu = prop.multiProcessorCount * std::min(occ_lu, 2);
+
+  // rigid box -> excluded cells (hydro2d.hpp:409-416)
+  {
+    int* anyflag = s->flag + 1;
+    cudaMemsetAsync(anyflag, 0, sizeof(int), s->st);
+    k_excl_mask<<<nblk(nc), 256, 0, s->st>>>(g, cfg->box_A[0], cfg->box_A[1], cfg->box_A[2], cfg->box_B[0], cfg->box_B[1], cfg->box_B[2], s->excl, anyflag);
+    ++s->launches;
+    int h = 0; cudaMemcpyAsync(&h, anyflag, sizeof(int), cudaMemcpyDeviceToHost, s->st); cudaStreamSynchronize(s->st);
+    s->any_excl = h != 0;
+    g.excl = s->any_excl ? s->excl : nullptr;
+  }
+  // fixed pressure cell: FindNearestCell (mesh.hpp:411-420), first minimum in raw order
+  if (cfg->pressure_fixed_enable) {
+    long long best = 0; double bd = 0.;
+    for (int k = 0; k < s->n[2]; ++k) for (int j = 0; j < s->n[1]; ++j) for (int i = 0; i < s->n[0]; ++i) {
+      double x[3] = {g.lb[0] + (i + 0.5) * g.h[0], g.lb[1] + (j + 0.5) * g.h[1], dim > 2 ? g.lb[2] + (k + 0.5) * g.h[2] : 0.};
+      double sq = 0.; for (int d = 0; d < dim; ++d) { double e = x[d] - cfg->pressure_fixed_point[d]; sq += e * e; }
+      double dd = std::sqrt(sq);
+      long long c = i + g.sy * j + g.sz * k;
+      if (c == 0) { bd = dd; best = 0; } else if (dd < bd) { bd = dd; best = c; }
+    }
+    g.pfix = best;
+  }
+  s->dt = cfg->dt; s->dt_adv = cfg->dt * cfg->advection_dt_factor;
+
+  // initial fields
+  {
+    InitArgs a; memset(&a, 0, sizeof a);
+    for (int d = 0; d < 3; ++d) {
+      a.v0[d] = cfg->initial_velocity[d]; a.sin_n[d] = cfg->initial_sin_n[d];
+      a.A1[d] = cfg->A1[d]; a.B1[d] = cfg->B1[d]; a.A2[d] = cfg->A2[d]; a.B2[d] = cfg->B2[d]; a.IC[d] = cfg->IC[d]; a.IC2[d] = cfg->IC2[d];
+      a.u[d] = d < dim ? s->u[L_TC][d] : s->w1;
+    }
+    a.pois = cfg->initial_pois; a.sin_on = cfg->initial_sin_enable; a.sin_lambda = cfg->initial_sin_lambda; a.sin_phase = cfg->initial_sin_phase;
+    a.IR = cfg->IR; a.IR2 = cfg->IR2; a.np = cfg->num_phases;
+    for (int p = 0; p < 3; ++p) { a.density[p] = cfg->density[p]; a.ivf[p] = cfg->initial_volume_fraction[p]; a.pd[p] = p < cfg->num_phases ? s->pd[p][L_TC] : s->w1; }
+    DIMSEL(s, k_init_fields, nblk(nc), 256, g, a);
+    for (int ph = 1; ph < cfg->num_phases; ++ph) {
+      if (cfg->initial_volume_fraction_smooth_times > 0) {
+        if (smooth_field(s, s->pd[ph][L_TC], cfg->initial_volume_fraction_smooth_times, s->w1)) return fail_create(s, HG_ERR_CUDA, s->err);
+        cudaMemcpyAsync(s->pd[ph][L_TC], s->w1, nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st);
+      }
+    }
+    LAUNCH(s, k_pd0, nblk(nc), 256, cfg->num_phases, cfg->density[0], cfg->density[1], cfg->density[2],
+           cfg->num_phases > 1 ? s->pd[1][L_TC] : s->zero, cfg->num_phases > 2 ? s->pd[2][L_TC] : s->zero, s->pd[0][L_TC], nc);
+    for (int ph = 0; ph < cfg->num_phases; ++ph) {
+      cudaMemcpyAsync(s->pd_init[ph], s->pd[ph][L_TC], nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st);
+      cudaMemcpyAsync(s->pd[ph][L_TP], s->pd[ph][L_TC], nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st);
+    }
+    for (int d = 0; d < dim; ++d) cudaMemcpyAsync(s->u[L_TP][d], s->u[L_TC][d], nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st);
+    CP3 uu; for (int d = 0; d < 3; ++d) uu.p[d] = d < dim ? s->u[L_TC][d] : s->zero;
+    DIMSEL(s, k_init_flux, nblk(nc), 256, g, uu, cfg->meshvel[0], cfg->meshvel[1], cfg->meshvel[2], s->F[L_TC]);
+    cudaMemcpyAsync(s->F[L_TP], s->F[L_TC], nf * sizeof(double), cudaMemcpyDeviceToDevice, s->st);
+    if (cfg->heat_enable) {
+      LAUNCH(s, k_fill, nblk(nc), 256, s->T[L_TC], cfg->temperature_initial, nc);
+      LAUNCH(s, k_fill, nblk(nc), 256, s->T[L_TP], cfg->temperature_initial, nc);
+    }
+  }
+  if (hg_update_properties(s) || hg_calc_stat(s, nullptr)) return fail_create(s, HG_ERR_CUDA, s->err);
+  if (cudaStreamSynchronize(s->st) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+    return fail_create(s, HG_ERR_CUDA, std::string("initialisation failed: ") + cudaGetErrorString(cudaGetLastError()));
+  *out = s;
+  return 0;
+}
+
+extern "C" int hg_destroy(hg_handle s) {
+  if (!s) return 0;
+  cudaSetDevice(s->dev);
+  cudaStreamSynchronize(s->st);
+  for (void* p : s->allocs) cudaFree(p);
+  if (s->hscal) cudaFreeHost(s->hscal);
+  if (s->hdiffs) cudaFreeHost(s->hdiffs);
+  for (auto& kv : s->timers) { if (kv.second.a) { cudaEventDestroy(kv.second.a); cudaEventDestroy(kv.second.b); } }
+  cudaStreamDestroy(s->st);
+  delete s;
+  return 0;
+}
+
+extern "C" const char* hg_last_error(hg_handle s) { return s ? s->err.c_str() : g_create_err.c_str(); }
+extern "C" size_t hg_num_cells(hg_handle s) { return s ? (size_t)s->nc : 0; }
+extern "C" size_t hg_num_faces(hg_handle s) { return s ? (size_t)s->nf : 0; }
+extern "C" long long hg_launch_count(hg_handle s) { return s ? s->launches : 0; }
+extern "C" int hg_device_synchronize(hg_handle s) {
+  if (!s) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  CK(cudaStreamSynchronize(s->st));
+  return 0;
+}
+
+static double* field_ptr(hg_state* s, int field, int layer, long long* n) {
+  *n = s->nc;
+  const int np = s->cfg.num_phases, dim = s->dim;
+  if (field >= HG_F_VELOCITY_X && field <= HG_F_VELOCITY_Z) return field - HG_F_VELOCITY_X < dim ? s->u[layer][field - HG_F_VELOCITY_X] : nullptr;
+  if (field >= HG_F_VELOCITY_PREV_X && field <= HG_F_VELOCITY_PREV_Z) return field - HG_F_VELOCITY_PREV_X < dim ? s->u[L_TP][field - HG_F_VELOCITY_PREV_X] : nullptr;
+  if (field == HG_F_PRESSURE) return s->p[layer];
+  if (field == HG_F_PRESSURE_PREV) return s->p[L_TP];
+  if (field == HG_F_VOLUME_FLUX) { *n = s->nf; return s->F[layer]; }
+  if (field == HG_F_VOLUME_FLUX_PREV) { *n = s->nf; return s->F[L_TP]; }
+  if (field >= HG_F_PARTIAL_DENSITY_0 && field <= HG_F_PARTIAL_DENSITY_2) return field - HG_F_PARTIAL_DENSITY_0 < np ? s->pd[field - HG_F_PARTIAL_DENSITY_0][layer] : nullptr;
+  if (field == HG_F_TEMPERATURE) return s->cfg.heat_enable ? s->T[layer] : nullptr;
+  if (field == HG_F_DENSITY) return s->rho;
+  if (field == HG_F_VISCOSITY) return s->mu;
+  if (field == HG_F_CONDUCTIVITY) return s->kc;
+  if (field >= HG_F_FORCE_X && field <= HG_F_FORCE_Z) return field - HG_F_FORCE_X < dim ? s->force[field - HG_F_FORCE_X] : nullptr;
+  if (field >= HG_F_STFORCE_X && field <= HG_F_STFORCE_Z) return field - HG_F_STFORCE_X < dim ? s->stforce[field - HG_F_STFORCE_X] : nullptr;
+  if (field >= HG_F_VOLUME_FRACTION_0 && field <= HG_F_VOLUME_FRACTION_2) return field - HG_F_VOLUME_FRACTION_0 < np ? s->vf[field - HG_F_VOLUME_FRACTION_0] : nullptr;
+  return nullptr;
+}
+
+extern "C" int hg_set_field(hg_handle s, int field, const double* src, size_t n) {
+  if (!s || !src) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  long long m; double* p = field_ptr(s, field, L_TC, &m);
+  if (!p || (long long)n != m || field == HG_F_EXCLUDED) { s->err = "hg_set_field: bad field id or size"; return HG_ERR_INVALID; }
+  CK(cudaMemcpyAsync(p, src, n * sizeof(double), cudaMemcpyHostToDevice, s->st));
+  if (field <= HG_F_TEMPERATURE) {
+    double* q = field_ptr(s, field, L_TP, &m);
+    CK(cudaMemcpyAsync(q, src, n * sizeof(double), cudaMemcpyHostToDevice, s->st));
+  }
+  CK(cudaStreamSynchronize(s->st));
+  return 0;
+}
+
+extern "C" int hg_get_field(hg_handle s, int field, double* dst, size_t n) {
+  if (!s || !dst) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  if (field == HG_F_EXCLUDED) {
+    if ((long long)n != s->nc) { s->err = "hg_get_field: bad size"; return HG_ERR_INVALID; }
+    LAUNCH(s, k_mask_to_double, nblk(s->nc), 256, s->any_excl ? s->excl : (const unsigned char*)nullptr, s->w1, s->nc);
+    CK(cudaMemcpyAsync(dst, s->w1, n * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    CK(cudaStreamSynchronize(s->st));
+    return 0;
+  }
+  long long m; double* p = field_ptr(s, field, L_TC, &m);
+  if (!p || (long long)n != m) { s->err = "hg_get_field: bad field id or size"; return HG_ERR_INVALID; }
+  CK(cudaMemcpyAsync(dst, p, n * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+  CK(cudaStreamSynchronize(s->st));
+  return 0;
+}
+
+// ------------------------------------------------------------------ kernel-level entries
+extern "C" int hg_interp_grad(hg_handle s, const double* u, int cond, int comp, double* gx, double* gy, double* gz) {
+  if (!s || !u || !gx || !gy) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  CK(cudaMemcpyAsync(s->w1, u, s->nc * sizeof(double), cudaMemcpyHostToDevice, s->st));
+  P3 out; for (int d = 0; d < 3; ++d) out.p[d] = s->G[d];
+  const unsigned gb = nblk(s->nc);
+  if (s->dim == 3) {
+    if (cond == 0) k_interp_grad<3, K_NEUMANN0><<<gb, 256, 0, s->st>>>(s->geo, s->w1, comp, out);
+    else if (cond == 1) k_interp_grad<3, K_EXTRAP><<<gb, 256, 0, s->st>>>(s->geo, s->w1, comp, out);
+    else k_interp_grad<3, K_VEL><<<gb, 256, 0, s->st>>>(s->geo, s->w1, comp, out);
+  } else {
+    if (cond == 0) k_interp_grad<2, K_NEUMANN0><<<gb, 256, 0, s->st>>>(s->geo, s->w1, comp, out);
+    else if (cond == 1) k_interp_grad<2, K_EXTRAP><<<gb, 256, 0, s->st>>>(s->geo, s->w1, comp, out);
+    else k_interp_grad<2, K_VEL><<<gb, 256, 0, s->st>>>(s->geo, s->w1, comp, out);
+  }
+  ++s->launches;
+  double* dst[3] = {gx, gy, gz};
+  for (int d = 0; d < s->dim; ++d) if (dst[d]) CK(cudaMemcpyAsync(dst[d], s->G[d], s->nc * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+  CK(cudaStreamSynchronize(s->st));
+  return 0;
+}
+
+extern "C" int hg_smooth_field(hg_handle s, const double* u, int repeat, double* out) {
+  if (!s || !u || !out) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  CK(cudaMemcpyAsync(s->w1, u, s->nc * sizeof(double), cudaMemcpyHostToDevice, s->st));
+  if (int rc = smooth_field(s, s->w1, repeat, s->pc)) return rc;
+  CK(cudaMemcpyAsync(out, s->pc, s->nc * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+  CK(cudaStreamSynchronize(s->st));
+  return 0;
+}
+
+extern "C" int hg_linear_solve(hg_handle s, int solver, const double* const coeffs[7], const double* rhs, double* x,
+                               double tol, int limit, double relax, int* out_iters, double* out_diff) {
+  if (!s || !coeffs || !rhs || !x) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  const unsigned gb = nblk(s->nc);
+  // rows and constants: host natural layout -> device sheared layout
+  for (int t = 0; t < 7; ++t) {
+    if (s->dim == 2 && (t == CZM || t == CZP)) continue;
+    if (!coeffs[t]) { s->err = "hg_linear_solve: missing coefficient array"; return HG_ERR_INVALID; }
+    CK(cudaMemcpyAsync(s->w1, coeffs[t], s->nc * sizeof(double), cudaMemcpyHostToDevice, s->st));
+    DIMSEL(s, k_to_sheared, gb, 256, s->geo, s->w1, s->A[t]);
+  }
+  CK(cudaMemcpyAsync(s->w1, rhs, s->nc * sizeof(double), cudaMemcpyHostToDevice, s->st));
+  DIMSEL(s, k_to_sheared, gb, 256, s->geo, s->w1, s->R[0]);
+  int it = 0; double df = 0.;
+  if (solver == HG_LS_LU) {
+    if (int rc = solve_lu(s, 1)) return rc;
+    DIMSEL(s, k_from_sheared, gb, 256, s->geo, s->X[0], s->pc);
+  } else if (solver == HG_LS_GAUSS_SEIDEL) {
+    auto launch = [&](int sb, int se) -> int {
+      SorArgs a; for (int t = 0; t < 7; ++t) a.A[t] = s->A[t];
+      a.R = s->R[0]; a.X = s->PP; a.diff = s->diffs; a.s_begin = sb; a.s_end = se; a.omega = relax;
+      if (s->dim == 3) return coop_launch(s, k_sor_matrix_persistent<3>, s->grid_solver, s->geo, a);
+      return coop_launch(s, k_sor_matrix_persistent<2>, s->grid_solver, s->geo, a);
+    };
+    const int save = s->cfg.pressure_sweeps_per_check;
+    if (int rc = run_sor(s, s->PP, s->nsh, tol, limit, launch, &it, &df)) { s->cfg.pressure_sweeps_per_check = save; return rc; }
+    DIMSEL(s, k_from_sheared, gb, 256, s->geo, s->PP, s->pc);
+  } else if (solver == HG_LS_JACOBI) {
+    // natural-layout rows in G[0..6] (dim*dim >= 4; use A-sized scratch via from_sheared)
+    double* nat[7];
+    double* pool[7] = {s->gp[0], s->gp[1], s->fcr[0], s->fcr[1], s->fs[0], s->fs[1], s->G[0]};
+    for (int t = 0; t < 7; ++t) {
+      nat[t] = pool[t];
+      if (s->dim == 2 && (t == CZM || t == CZP)) continue;
+      DIMSEL(s, k_from_sheared, gb, 256, s->geo, s->A[t], nat[t]);
+    }
+    DIMSEL(s, k_from_sheared, gb, 256, s->geo, s->R[0], s->w1);
+    if (int rc = run_jacobi(s, nat, nullptr, s->w1, tol, limit, relax, &it, &df)) return rc;
+  } else {
+    s->err = "hg_linear_solve: solver not on the GPU path";
+    return HG_ERR_INVALID;
+  }
+  CK(cudaMemcpyAsync(x, s->pc, s->nc * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+  CK(cudaStreamSynchronize(s->st));
+  if (out_iters) *out_iters = it;
+  if (out_diff) *out_diff = df;
+  return 0;
+}
+
+extern "C" int hg_last_residuals(hg_handle s, double* out, int cap, int* n) {
+  if (!s || !out || !n) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  int m = s->iter_count < cap ? s->iter_count : cap;
+  if (m > 4096) m = 4096;
+  if (m > 0) { CK(cudaMemcpyAsync(out, s->resid, m * sizeof(double), cudaMemcpyDeviceToHost, s->st)); CK(cudaStreamSynchronize(s->st)); }
+  *n = m;
+  return 0;
+}
+
+extern "C" int hg_timers_enable(hg_handle s, int enable) {
+  if (!s) return HG_ERR_INVALID;
+  s->timers_on = enable != 0;
+  return 0;
+}
+extern "C" int hg_timers(hg_handle s, char (*names)[64], double* seconds, int cap, int* n) {
+  if (!s || !n) return HG_ERR_INVALID;
+  int k = 0;
+  for (auto& kv : s->timers) {
+    if (k >= cap) break;
+    if (names) { strncpy(names[k], kv.first.c_str(), 63); names[k][63] = 0; }
+    if (seconds) seconds[k] = kv.second.total;
+    ++k;
+  }
+  *n = k;
+  return 0;
+}

@@ -189,6 +189,9 @@ int hg_fluid_start_step(hg_handle h);
 int hg_fluid_make_iteration(hg_handle h);
 int hg_fluid_convergence_indicator(hg_handle h, double* out);
 int hg_fluid_is_converged(hg_handle h, int* out);
+/* convergence indicator of every SIMPLE iteration of the current/last step (the `Rs=` values the
+ * reference logs, hydro2d.hpp:1585-1586); at most `cap`, count in *n */
+int hg_last_residuals(hg_handle h, double* out, int cap, int* n);
 int hg_fluid_finish_step(hg_handle h);
 int hg_fluid_auto_time_step(hg_handle h, double* out);      /* FluidSimple::GetAutoTimeStep fluid.hpp:1191 */
 int hg_set_time_step(hg_handle h, double dt_fluid, double dt_advection);

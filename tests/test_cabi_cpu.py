@@ -1,0 +1,97 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/hydro_gpu.h
+declares; the ctypes structs match the C structs; parameter parsing mirrors the reference's names;
+hg_create refuses to run without a device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import cases
+from hydro_b200 import capi
+from hydro_b200.config import HgConfig, HgStepStats, Params
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "hydro_gpu.h")).read()
+    return sorted(set(re.findall(r"\b(hg_[a-z_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load_library()
+    syms = declared_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert set(capi.SYMBOLS) <= set(syms)
+
+
+def test_struct_layout_matches_header(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hydro_gpu.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
+                   'sizeof(hg_config),sizeof(hg_step_stats),offsetof(hg_config,num_phases),offsetof(hg_config,world_size),'
+                   'offsetof(hg_step_stats,center));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert out == [C.sizeof(HgConfig), C.sizeof(HgStepStats), HgConfig.num_phases.offset, HgConfig.world_size.offset,
+                   HgStepStats.center.offset]
+
+
+def test_defaults_match_general_hydroconf():
+    lib = capi.load_library()
+    c = HgConfig()
+    lib.hg_config_defaults(C.byref(c))
+    p = Params().to_struct()
+    for name, _ in HgConfig._fields_:
+        a, b = getattr(c, name), getattr(p, name)
+        if hasattr(a, "__len__"):
+            a, b = [list(x) if hasattr(x, "__len__") else x for x in a], [list(x) if hasattr(x, "__len__") else x for x in b]
+        assert a == b, name
+
+
+def test_params_parse_hydroconf_text():
+    p = Params()
+    p.read_hydroconf("""
+        set string MODULE hydro3d
+        set int Nx 16   # comment
+        set vect B (3.2, 1, 1)
+        set double dt 0.0025
+        set string condition_top "wall 1 0 0"
+        set vect pressure_fixed_point (0, 1, 0)
+        set int max_frame_index $(Nx)0
+        del pressure_fixed_point
+    """)
+    c = p.to_struct()
+    assert (c.dim, c.Nx, c.dt) == (3, 16, 0.0025)
+    assert list(c.B) == [3.2, 1.0, 1.0]
+    assert list(c.condition_velocity[3]) == [1.0, 0.0, 0.0]
+    assert c.pressure_fixed_enable == 0 and p["max_frame_index"] == 160
+
+
+def test_missing_parameter_raises_like_reference():
+    p = Params()
+    del p["Nx"]
+    with pytest.raises(KeyError, match="'Nx' undefined"):
+        p.to_struct()
+    with pytest.raises(ValueError, match="Unknown linear solver"):
+        Params(linear_solver_pressure="pardiso").to_struct()
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        capi.Hydro(cases.cavity(8))
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "hydro_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+\S*oracle|liboracle|#include\s+\"[^\"]*oracle|dlopen", txt, re.M), f

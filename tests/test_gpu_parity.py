@@ -1,0 +1,206 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference fixtures.
+
+Tolerances: the device code keeps the reference's operation order and is compiled without FMA
+contraction, so fields agree with the oracle to rounding; the stated bound is 1e-12 relative L2 per
+field after the case's steps (north_star: "relative L2 of velocity/pressure/scalar after N steps"),
+equal SIMPLE-iteration counts and equal linear-solver sweep counts.  CalcStat sums are parallel
+reductions: 1e-11 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from hydro_b200.config import F
+from oracle_api import Oracle
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-12
+
+FIELDS = ["VELOCITY_X", "VELOCITY_Y", "VELOCITY_Z", "PRESSURE", "VOLUME_FLUX", "DENSITY", "VISCOSITY",
+          "PARTIAL_DENSITY_0", "PARTIAL_DENSITY_1", "VOLUME_FRACTION_0", "FORCE_X", "FORCE_Y", "TEMPERATURE",
+          "VELOCITY_PREV_X", "PRESSURE_PREV", "VOLUME_FLUX_PREV", "EXCLUDED"]
+GOLD_KEYS = {"VELOCITY_X": "u0", "VELOCITY_Y": "u1", "VELOCITY_Z": "u2", "PRESSURE": "p", "VOLUME_FLUX": "flux",
+             "PARTIAL_DENSITY_0": "pd0", "PARTIAL_DENSITY_1": "pd1", "TEMPERATURE": "temp", "DENSITY": "rho",
+             "VISCOSITY": "mu"}
+
+
+def rel_l2(a, b):
+    n = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / (n if n > 0 else 1.0)
+
+
+def has_field(o, name):
+    if name.endswith("_Z") and o.dim == 2:
+        return False
+    if name == "TEMPERATURE" and not o.cfg.heat_enable:
+        return False
+    if name[-1] in "12" and name[:-2] in ("PARTIAL_DENSITY", "VOLUME_FRACTION") and int(name[-1]) >= o.cfg.num_phases:
+        return False
+    return True
+
+
+def compare_states(gpu, cpu, tol=TOL):
+    for name in FIELDS:
+        if not has_field(cpu, name):
+            continue
+        a, b = gpu.get(name), cpu.get(name)
+        assert np.all(np.isfinite(a)), name
+        assert rel_l2(a, b) <= tol, (name, rel_l2(a, b))
+
+
+def run_both(p, nsteps, tol=TOL):
+    from hydro_b200.capi import Hydro
+    gpu, cpu = Hydro(p), Oracle(p)
+    compare_states(gpu, cpu, tol)   # initial state (module constructor)
+    for _ in range(nsteps):
+        sg, sc = gpu.step(), cpu.step()
+        assert sg.simple_iterations == sc.simple_iterations
+        assert sg.pressure_sweeps_total == sc.pressure_sweeps_total
+        assert sg.advection_substeps == sc.advection_substeps
+        rg, rc = gpu.residuals(), cpu.residuals()
+        assert len(rg) == len(rc)
+        np.testing.assert_allclose(rg, rc, rtol=1e-9, atol=1e-300)
+        np.testing.assert_allclose(sg.dt, sc.dt, rtol=1e-13)
+        np.testing.assert_allclose(sg.pressure_last_diff, sc.pressure_last_diff, rtol=1e-8, atol=1e-300)
+        for i in range(cpu.cfg.num_phases):
+            np.testing.assert_allclose([sg.volume[i], sg.mass[i], sg.pd_min[i], sg.pd_max[i], *sg.center[i], *sg.velocity[i]],
+                                       [sc.volume[i], sc.mass[i], sc.pd_min[i], sc.pd_max[i], *sc.center[i], *sc.velocity[i]],
+                                       rtol=1e-11, atol=1e-14)
+    compare_states(gpu, cpu, tol)
+    return gpu, cpu
+
+
+@pytest.mark.parametrize("name", list(cases.GOLDEN_CASES))
+def test_gpu_matches_oracle_and_reference_fixture(name):
+    p, nsteps = cases.GOLDEN_CASES[name]
+    if p["linear_solver_pressure"] == "lu_relaxed":
+        pytest.skip("lu_relaxed is not on the GPU path yet (SURVEY 8f rank 4)")
+    gpu, cpu = run_both(p, nsteps)
+    g = np.load(os.path.join(GOLD, "ref_%s.npz" % name))
+    for fname, key in GOLD_KEYS.items():
+        if key in g.files and has_field(cpu, fname):
+            assert rel_l2(gpu.get(fname), g[key]) <= 1e-11, (fname, rel_l2(gpu.get(fname), g[key]))
+
+
+def test_gpu_cavity_sample_first_iterations():
+    """The reference's golden sample (examples/cavity/sample): the first 60 SIMPLE residuals printed
+    with 6 significant digits must equal the shipped exp.iter_history.plt tokens."""
+    from hydro_b200.capi import Hydro
+    g = np.load(os.path.join(GOLD, "cavity_sample.npz"))
+    p = cases.cavity_kat()
+    p["num_iterations_limit"] = 60
+    gpu = Hydro(p)
+    gpu.step()
+    tok = np.array(["%g" % v for v in gpu.residuals()])
+    assert np.array_equal(tok, g["rs_tokens"][:60])
+
+
+@pytest.mark.parametrize("n", [32, 48])
+def test_gpu_rt3d_medium(n):
+    """W4 at sizes the oracle finishes in seconds; fixed work (3 SIMPLE x 101 sweeps)."""
+    run_both(cases.rt3d(n), 2)
+
+
+def test_gpu_dam3d_as_shipped():
+    """examples/broken_dam_3d as shipped (64x20x20, obstacle)."""
+    run_both(cases.broken_dam_3d(64, 20, 20, lu_relaxed_num_iters_limit=60), 2)
+
+
+def test_gpu_rt3d_early_stop_sweeps():
+    """tolerance > 0: the pipelined sweeps must stop at exactly the reference's sweep count."""
+    run_both(cases.rt3d(12, fixed_work=False, lu_relaxed_num_iters_limit=300, lu_relaxed_tolerance=1e-7,
+                        num_iterations_limit=4, pressure_sweeps_per_check=32), 2)
+
+
+def test_gpu_tvd_split_and_surface_tension():
+    run_both(cases.broken_dam_2d(40, 24, tvd_split=1, sigma=0.07, lu_relaxed_num_iters_limit=40), 2, tol=1e-11)
+
+
+def test_gpu_inlet_condition():
+    run_both(cases.thermal_2d(24, 12, condition_left="inlet 0.3 0 0", condition_right="inlet 0.3 0 0"), 2)
+
+
+# ---------------------------------------------------------------- kernel-level entries
+def sin_field(n):
+    return np.sin(np.arange(n, dtype=np.float64))   # test/benchmark/main.cpp:172 input pattern
+
+
+@pytest.mark.parametrize("case", ["rt3d_12x10x9", "dam3d_32x10x10", "cavity_16"])
+@pytest.mark.parametrize("cond", [0, 1, 2])
+def test_interp_grad(case, cond):
+    from hydro_b200.capi import Hydro
+    p, _ = cases.GOLDEN_CASES[case]
+    gpu, cpu = Hydro(p), Oracle(p)
+    u = sin_field(cpu.nc)
+    for a, b in zip(gpu.interp_grad(u, cond, 1), cpu.interp_grad(u, cond, 1)):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("case", ["rt3d_12x10x9", "dam3d_32x10x10", "cavity_16"])
+def test_smooth_field(case):
+    from hydro_b200.capi import Hydro
+    p, _ = cases.GOLDEN_CASES[case]
+    gpu, cpu = Hydro(p), Oracle(p)
+    u = sin_field(cpu.nc)
+    for rep in (0, 1, 3):
+        assert np.array_equal(gpu.smooth_field(u, rep), cpu.smooth_field(u, rep))
+
+
+def random_rows(o, seed):
+    """Diagonally dominant 7/5-point rows in the reference's term order z-,y-,x-,diag,x+,y+,z+."""
+    rng = np.random.default_rng(seed)
+    nc = o.nc
+    rows = [-rng.random(nc) for _ in range(7)]
+    rows[3] = 6.5 + rng.random(nc)
+    if o.dim == 2:
+        rows[0] = rows[6] = None
+    return rows, rng.standard_normal(nc)
+
+
+@pytest.mark.parametrize("case", ["rt3d_12x10x9", "cavity_16", "rt3d_16"])
+@pytest.mark.parametrize("solver,tol,limit", [("lu", 0.0, 0), ("gauss_seidel", 0.0, 40), ("gauss_seidel", 1e-6, 500),
+                                                ("jacobi", 1e-5, 300), ("jacobi", 0.0, 21)])
+def test_linear_solve(case, solver, tol, limit):
+    from hydro_b200.capi import Hydro
+    p, _ = cases.GOLDEN_CASES[case]
+    gpu, cpu = Hydro(p), Oracle(p)
+    rows, rhs = random_rows(cpu, 7)
+    relax = 1.3 if solver == "gauss_seidel" else 0.8
+    xg, ig, dg = gpu.linear_solve(solver, rows, rhs, tol, limit, relax)
+    xc, ic, dc = cpu.linear_solve(solver, rows, rhs, tol, limit, relax)
+    assert ig == ic
+    assert np.array_equal(xg, xc)
+    if solver != "lu":
+        assert dg == dc
+
+
+def test_error_convention():
+    """Unsupported options fail in hg_create with a message instead of silently falling back."""
+    from hydro_b200.capi import Hydro
+    with pytest.raises(RuntimeError, match="simpler"):
+        Hydro(cases.cavity(8, simpler=1))
+    with pytest.raises(RuntimeError, match="outlet"):
+        Hydro(cases.cavity(8, condition_right="outlet"))
+    h = Hydro(cases.cavity(8))
+    with pytest.raises(RuntimeError, match="bad field"):
+        h.set("PRESSURE", np.zeros(3))
+    h.set("PRESSURE", np.full(h.nc, np.nan))
+    with pytest.raises(RuntimeError, match="NaN initial pressure"):
+        h.step()
+
+
+def test_set_get_roundtrip_and_idempotent_properties():
+    from hydro_b200.capi import Hydro
+    h = Hydro(cases.rt3d(8))
+    for name in ("VELOCITY_X", "PRESSURE", "VOLUME_FLUX", "PARTIAL_DENSITY_1"):
+        n = h.nf if F[name] == F["VOLUME_FLUX"] else h.nc
+        v = sin_field(n)
+        h.set(name, v)
+        assert np.array_equal(h.get(name), v)
+    h.update_properties()
+    a = h.get("DENSITY").copy()
+    h.update_properties()
+    assert np.array_equal(h.get("DENSITY"), a)
