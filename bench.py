@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py -- cell-updates/s per time step (pressure solve included) of hydro's hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--size n]
+
+Workload (BASELINE.json configs[3]): Rayleigh-Taylor 3-D, `examples/rt` parameters with
+MODULE hydro3d on a unit cube, n^3 cells (default 256^3), fixed work per step: 3 SIMPLE iterations x
+(lu momentum solve + 101 Gauss-Seidel sweeps) + 1 advection sub-step + properties + statistics.
+A "step" is one hydro<Mesh>::step() (hydro2d.hpp:1531-1621) through the C ABI.
+
+impl b200      : the CUDA path (libhydro_gpu.so).  `value` = whole-job cell-updates/s with the state resident
+                 in HBM; `e2e` = same through hg_set_field/hg_step/hg_get_field with pinned HOST buffers.
+impl reference : the UNMODIFIED reference binary (oracle/_ref/hydro, OpenMP, all host threads) on a bounded
+                 sample of the same workload (--cpu-size^3 cells), or the oracle port if it was not built.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+METRIC = "cell-updates/s per timestep incl. pressure solve"
+UNIT = "cell-updates/s"
+
+
+def workload_params(n):
+    import cases
+    return cases.rt3d(n, fixed_work=True)
+
+
+def bytes_per_cell_step(n_simple, sweeps_per_solve, n_adv, heat):
+    """Algorithmic HBM bytes per cell per step, SURVEY.md 8(d) / BASELINE.md section 3."""
+    return n_simple * (664 + 32 * sweeps_per_solve) + 96 * n_adv + (240 if heat else 0) + 120
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def measured_peak():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_run(n, steps, warmup):
+    """The reference's own CPU implementation on the box's host cores: returns (cell-updates/s, info)."""
+    import refrun
+    p = workload_params(n)
+    cells = n ** 3
+    cores = os.cpu_count() or 1
+    if os.access(refrun.REF_HYDRO, os.X_OK):
+        t_all, timers, _ = refrun.run_reference_binary(p, steps + warmup, threads=cores)
+        use = t_all[warmup:] if len(t_all) > warmup else t_all
+        sec = sum(use) / len(use)
+        info = {"kind": "reference", "cores": cores,
+                "sample": "RT-3D %d^3 fixed-work, %d timed steps after %d warm-up, unmodified reference binary "
+                          "(oracle/_ref/hydro, OpenMP %d threads; its linear solvers and advection are serial), "
+                          "per-step t_all from its log" % (n, len(use), warmup, cores),
+                "pressure_solve_share": (timers.get("fluid.6.pressure-solve", 0.) / timers["step"]) if timers.get("step") else None}
+    else:
+        from oracle_api import Oracle
+        o = Oracle(p, fast=True)
+        for _ in range(warmup):
+            o.step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            o.step()
+        sec = (time.perf_counter() - t0) / steps
+        info = {"kind": "port", "cores": 1,
+                "sample": "RT-3D %d^3 fixed-work, %d timed steps after %d warm-up, oracle/hydro_oracle.c "
+                          "(serial C restatement, -O3)" % (n, steps, warmup)}
+    return cells / sec, sec, info
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n = args.cpu_size
+    val, sec, info = cpu_reference_run(n, args.steps, max(args.warmup, 1))
+    info["value"] = val
+    info["unit"] = UNIT
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "RT-3D fixed-work (3 SIMPLE x 101 GS sweeps), bounded sample %d^3 on host cores" % n,
+                       "cells": n ** 3, "parallelism": "OpenMP x%d" % info["cores"]},
+            "cpu_baseline": info,
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_b200(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    from hydro_b200.capi import Hydro
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    n = args.size
+    p = workload_params(n)
+    h = Hydro(p, device=local_rank)
+    cells = h.nc
+    K, W = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        h.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches0 = None
+    for _ in range(W):
+        st = h.step()
+    n_simple, sweeps, n_adv = st.simple_iterations, st.pressure_sweeps_total, st.advection_substeps
+    # ---- device-resident timing
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    h.profile_enable(True)
+    h.profile_read(0), h.profile_read(1)
+    barrier()
+    launches0 = h.launch_count()
+    h.event_record(0)
+    for _ in range(K):
+        st = h.step()
+    h.event_record(1)
+    barrier()
+    ms = h.event_elapsed_ms(0, 1)
+    launches = h.launch_count() - launches0
+    gs_n, gs_ms = h.profile_read(0)
+    lu_n, lu_ms = h.profile_read(1)
+    h.profile_enable(False)
+    clocks = sampler.stop() if sampler else None
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sec_step = ms * 1e-3 / K
+    value = world * cells / sec_step
+
+    # ---- end to end through the C ABI with pinned host buffers (SURVEY 8b secondary boundary: the
+    # fields FluidSimple reads from caller memory every iteration, hydro2d.hpp:449-463, are uploaded each step;
+    # velocity + pressure are downloaded each step, as write_results / CalcStat consume them)
+    ins = ["DENSITY", "VISCOSITY", "FORCE_X", "FORCE_Y", "FORCE_Z"]
+    outs = ["VELOCITY_X", "VELOCITY_Y", "VELOCITY_Z", "PRESSURE"]
+    pin_in = {k: torch.empty(cells, dtype=torch.float64).pin_memory() for k in ins}
+    pin_out = {k: torch.empty(cells, dtype=torch.float64).pin_memory() for k in outs}
+    for k in ins:
+        h.get_to(k, pin_in[k].data_ptr())
+    Ke = max(2, min(K, 3))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        for k in ins:
+            h.set_from(k, pin_in[k].data_ptr())
+        st2 = h.step()
+        for k in outs:
+            h.get_to(k, pin_out[k].data_ptr())
+    barrier()
+    e2e_sec = (time.perf_counter() - t0) / Ke
+    if dist is not None:
+        t = torch.tensor([e2e_sec], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_sec = float(t.item())
+    e2e = {"value": world * cells / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": len(ins) * cells * 8,
+           "d2h_bytes_per_step": len(outs) * cells * 8 + 8 * 40, "ms_per_step": e2e_sec * 1e3, "steps": Ke,
+           "timing": "host wall clock around pinned H2D + hg_step + D2H, stream-synchronised, max over ranks"}
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    # roofline of the dominant kernel: the pipelined Gauss-Seidel sweep kernel (k_gs_persistent), one launch
+    # per pressure solve = (limit+1) sweeps x 32 algorithmic bytes per cell-sweep
+    sweeps_per_solve = p["lu_relaxed_num_iters_limit"] + 1
+    gs_bytes = 32.0 * sweeps_per_solve * cells
+    gs_avg_ms = gs_ms / gs_n if gs_n else float("nan")
+    achieved = gs_bytes / (gs_avg_ms * 1e-3) / 1e9 if gs_n else None
+    bpcs = bytes_per_cell_step(n_simple, sweeps_per_solve, n_adv, False)
+    step_gbs = bpcs * cells / sec_step / 1e9
+    roof = {"bound": "hbm", "kernel": "k_gs_persistent<3> (pipelined lexicographic Gauss-Seidel/SOR, %d sweeps per launch)" % sweeps_per_solve,
+            "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+            "frac": achieved / peak if achieved else None, "traffic": None,
+            "launches_timed": gs_n, "avg_launch_ms": gs_avg_ms, "share_of_step": gs_ms / ms if ms else None,
+            "lu_kernel_share_of_step": lu_ms / ms if ms else None,
+            "whole_step": {"algorithmic_bytes_per_cell_step": bpcs, "achieved": step_gbs, "frac": step_gbs / peak}}
+    traffic_file = os.path.join(ROOT, "profiles", "gs_traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roof["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch_scaled_to", {}).get(str(n))
+        except Exception:
+            pass
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            v, sec, info = cpu_reference_run(args.cpu_size, 2, 1)
+            info.update({"value": v, "unit": UNIT, "ms_per_step": sec * 1e3})
+            cpu = info
+        except Exception as e:  # the baseline is a report, never a gate
+            cpu = {"error": str(e)[:200]}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": sec_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "RT-3D %d^3 fixed-work: 3 SIMPLE iterations x (lu momentum + 101 GS sweeps) + 1 advection "
+                                   "sub-step + properties + stats per step (SURVEY 8d W4)" % n,
+                       "cells_per_gpu": cells, "simple_iterations": n_simple, "pressure_sweeps_per_step": sweeps,
+                       "advection_substeps": n_adv,
+                       "parallelism": "1 GPU" if world == 1 else "%d independent replicas (weak)" % world,
+                       "l2": "working set %.1f GB per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)" % (cells * 8 * 90 / 1e9)},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--cpu-size", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

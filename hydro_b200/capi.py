@@ -24,7 +24,8 @@ SYMBOLS = [
     "hg_fluid_convergence_indicator", "hg_fluid_is_converged", "hg_last_residuals", "hg_fluid_finish_step",
     "hg_fluid_auto_time_step", "hg_set_time_step", "hg_advection_step", "hg_heat_step",
     "hg_update_properties", "hg_calc_stat", "hg_interp_grad", "hg_linear_solve", "hg_smooth_field",
-    "hg_timers", "hg_timers_enable", "hg_launch_count", "hg_device_synchronize",
+    "hg_timers", "hg_timers_enable", "hg_launch_count", "hg_device_synchronize", "hg_event_record",
+    "hg_event_elapsed_ms", "hg_profile_enable", "hg_profile_read",
 ]
 
 
@@ -65,6 +66,10 @@ def load_library():
     l.hg_smooth_field.argtypes = [C.c_void_p, dp, C.c_int, dp]
     l.hg_timers.argtypes = [C.c_void_p, C.c_void_p, dp, C.c_int, C.POINTER(C.c_int)]
     l.hg_timers_enable.argtypes = [C.c_void_p, C.c_int]
+    l.hg_event_record.argtypes = [C.c_void_p, C.c_int]
+    l.hg_event_elapsed_ms.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
+    l.hg_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    l.hg_profile_read.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), dp]
     l.hg_launch_count.argtypes = [C.c_void_p]
     l.hg_launch_count.restype = C.c_longlong
     _lib = l
@@ -210,6 +215,37 @@ class Hydro:
         n = C.c_int()
         self._chk(self.l.hg_timers(self.h, C.cast(names, C.c_void_p), secs, 64, C.byref(n)))
         return {names[i].value.decode(): secs[i] for i in range(n.value)}
+
+    def event_record(self, slot):
+        self._chk(self.l.hg_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        v = C.c_double()
+        self._chk(self.l.hg_event_elapsed_ms(self.h, a, b, C.byref(v)))
+        return v.value
+
+    def profile_enable(self, on=True):
+        self._chk(self.l.hg_profile_enable(self.h, int(on)))
+
+    def profile_read(self, which):
+        n = C.c_int()
+        ms = C.c_double()
+        self._chk(self.l.hg_profile_read(self.h, which, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+    def get_into(self, name, buf):
+        """hg_get_field into a caller-provided (e.g. pinned) float64 buffer."""
+        fid = F[name] if isinstance(name, str) else name
+        self._chk(self.l.hg_get_field(self.h, fid, C.cast(buf.ctypes.data if hasattr(buf, "ctypes") else buf, C.POINTER(C.c_double)), self.nf if fid in FACE_FIELDS else self.nc))
+
+    def set_from(self, name, ptr):
+        """hg_set_field from a raw host pointer (int) of nc/nf doubles (e.g. pinned torch tensor)."""
+        fid = F[name] if isinstance(name, str) else name
+        self._chk(self.l.hg_set_field(self.h, fid, C.cast(ptr, C.POINTER(C.c_double)), self.nf if fid in FACE_FIELDS else self.nc))
+
+    def get_to(self, name, ptr):
+        fid = F[name] if isinstance(name, str) else name
+        self._chk(self.l.hg_get_field(self.h, fid, C.cast(ptr, C.POINTER(C.c_double)), self.nf if fid in FACE_FIELDS else self.nc))
 
     def launch_count(self):
         return int(self.l.hg_launch_count(self.h))

@@ -55,6 +55,9 @@ struct hg_state {
   std::map<std::string, Timer> timers;
   std::vector<std::string> timer_stack;
   std::vector<void*> allocs;
+  bool profile_on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[2];   // [0] pressure sweeps kernel, [1] lu kernel
+  cudaEvent_t user_ev[8] = {};
   std::string err;
 };
 
@@ -127,9 +130,12 @@ static void bdf_coeffs(double dt, int second_order, double co[3]) {
 
 // ------------------------------------------------------------------ solvers (host side)
 template <class K, class A>
-static int coop_launch(hg_state* s, K kern, int grid, Geo g, A args) {
+static int coop_launch(hg_state* s, K kern, int grid, Geo g, A args, int prof_slot = -1) {
   void* params[] = {(void*)&g, (void*)&args};
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (s->profile_on && prof_slot >= 0) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s->st); }
   CK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(SOLVER_THREADS), params, 0, s->st));
+  if (e0) { cudaEventRecord(e1, s->st); s->prof_ev[prof_slot].push_back({e0, e1}); }
   ++s->launches;
   return 0;
 }
@@ -248,8 +254,8 @@ static int solve_pressure(hg_state* s) {
     auto launch = [&](int sb, int se) -> int {
       GsArgs a; a.D = s->D; a.RP = s->RP; a.PP = s->PP; a.diff = s->diffs; a.s_begin = sb; a.s_end = se;
       a.omega = c.lu_relaxed_relaxation_factor;
-      if (s->dim == 3) return coop_launch(s, k_gs_persistent<3>, s->grid_solver, s->geo, a);
-      return coop_launch(s, k_gs_persistent<2>, s->grid_solver, s->geo, a);
+      if (s->dim == 3) return coop_launch(s, k_gs_persistent<3>, s->grid_solver, s->geo, a, 0);
+      return coop_launch(s, k_gs_persistent<2>, s->grid_solver, s->geo, a, 0);
     };
     if (int rc = run_sor(s, s->PP, s->nsh, c.lu_relaxed_tolerance, c.lu_relaxed_num_iters_limit, launch, &it, &df)) return rc;
     DIMSEL(s, k_pcorr, nblk(s->nc), 256, s->geo, s->PP, s->p[L_IP], c.pressure_relaxation_factor, s->pc, s->p[L_IC]);
@@ -274,8 +280,8 @@ static int solve_lu(hg_state* s, int ncomp) {
   for (int t = 0; t < 7; ++t) a.A[t] = s->A[t];
   for (int n = 0; n < 3; ++n) { a.R[n] = s->R[n]; a.X[n] = s->X[n]; }
   a.ncomp = ncomp;
-  if (s->dim == 3) return coop_launch(s, k_lu_persistent<3>, s->grid_lu, s->geo, a);
-  return coop_launch(s, k_lu_persistent<2>, s->grid_lu, s->geo, a);
+  if (s->dim == 3) return coop_launch(s, k_lu_persistent<3>, s->grid_lu, s->geo, a, 1);
+  return coop_launch(s, k_lu_persistent<2>, s->grid_lu, s->geo, a, 1);
 }
 
 // ------------------------------------------------------------------ properties / statistics
@@ -970,6 +976,41 @@ extern "C" int hg_last_residuals(hg_handle s, double* out, int cap, int* n) {
   if (m > 4096) m = 4096;
   if (m > 0) { CK(cudaMemcpyAsync(out, s->resid, m * sizeof(double), cudaMemcpyDeviceToHost, s->st)); CK(cudaStreamSynchronize(s->st)); }
   *n = m;
+  return 0;
+}
+
+// ---- instrumentation: CUDA events on the handle's own stream (torch.cuda.Event only sees torch's stream)
+extern "C" int hg_event_record(hg_handle s, int slot) {
+  if (!s || slot < 0 || slot >= 8) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  if (!s->user_ev[slot]) CK(cudaEventCreate(&s->user_ev[slot]));
+  CK(cudaEventRecord(s->user_ev[slot], s->st));
+  return 0;
+}
+extern "C" int hg_event_elapsed_ms(hg_handle s, int slot_a, int slot_b, double* ms) {
+  if (!s || !ms || slot_a < 0 || slot_b < 0 || slot_a >= 8 || slot_b >= 8 || !s->user_ev[slot_a] || !s->user_ev[slot_b]) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  CK(cudaEventSynchronize(s->user_ev[slot_b]));
+  float f = 0.f; CK(cudaEventElapsedTime(&f, s->user_ev[slot_a], s->user_ev[slot_b]));
+  *ms = f;
+  return 0;
+}
+extern "C" int hg_profile_enable(hg_handle s, int enable) {
+  if (!s) return HG_ERR_INVALID;
+  s->profile_on = enable != 0;
+  return 0;
+}
+extern "C" int hg_profile_read(hg_handle s, int which, int* count, double* total_ms) {
+  if (!s || which < 0 || which > 1 || !count || !total_ms) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  CK(cudaStreamSynchronize(s->st));
+  double tot = 0.; int n = 0;
+  for (auto& pr : s->prof_ev[which]) {
+    float f = 0.f; cudaEventElapsedTime(&f, pr.first, pr.second); tot += f; ++n;
+    cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+  }
+  s->prof_ev[which].clear();
+  *count = n; *total_ms = tot;
   return 0;
 }
 

@@ -228,7 +228,12 @@ int hg_timers_enable(hg_handle h, int enable);
 /* counts kernels launched by this handle since creation (bench.py "gpu_launches") */
 long long hg_launch_count(hg_handle h);
 
-/* device/bench helpers */
+/* device/bench helpers: CUDA events recorded on the handle's own stream (8 slots), and per-launch
+ * timing of the two persistent solver kernels (which: 0 = pressure sweeps, 1 = lu); reading clears */
+int hg_event_record(hg_handle h, int slot);
+int hg_event_elapsed_ms(hg_handle h, int slot_a, int slot_b, double* ms);
+int hg_profile_enable(hg_handle h, int enable);
+int hg_profile_read(hg_handle h, int which, int* count, double* total_ms);
 int hg_device_synchronize(hg_handle h);
 
 #ifdef __cplusplus

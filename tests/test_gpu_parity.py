@@ -42,16 +42,35 @@ def has_field(o, name):
     return True
 
 
+def vector_scale(cpu, name):
+    """Components of a vector field are measured against the L2 norm of the whole vector field
+    ("relative L2 of velocity"): a component that is ~0 by symmetry has no scale of its own."""
+    for stem in ("VELOCITY_PREV_", "VELOCITY_", "FORCE_"):
+        if name.startswith(stem) and name[len(stem):] in ("X", "Y", "Z"):
+            comps = [cpu.get(stem + c) for c in "XYZ"[:cpu.dim]]
+            return np.sqrt(sum(np.linalg.norm(c) ** 2 for c in comps))
+    return None
+
+
+def field_error(gpu, cpu, name, ref=None):
+    a = gpu.get(name)
+    b = cpu.get(name) if ref is None else ref
+    assert np.all(np.isfinite(a)), name
+    sc = vector_scale(cpu, name)
+    if sc is None:
+        sc = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / (sc if sc > 0 else 1.0)
+
+
 def compare_states(gpu, cpu, tol=TOL):
     for name in FIELDS:
         if not has_field(cpu, name):
             continue
-        a, b = gpu.get(name), cpu.get(name)
-        assert np.all(np.isfinite(a)), name
-        assert rel_l2(a, b) <= tol, (name, rel_l2(a, b))
+        e = field_error(gpu, cpu, name)
+        assert e <= tol, (name, e)
 
 
-def run_both(p, nsteps, tol=TOL):
+def run_both(p, nsteps, tol=TOL, stat_tol=1e-11):
     from hydro_b200.capi import Hydro
     gpu, cpu = Hydro(p), Oracle(p)
     compare_states(gpu, cpu, tol)   # initial state (module constructor)
@@ -68,7 +87,7 @@ def run_both(p, nsteps, tol=TOL):
         for i in range(cpu.cfg.num_phases):
             np.testing.assert_allclose([sg.volume[i], sg.mass[i], sg.pd_min[i], sg.pd_max[i], *sg.center[i], *sg.velocity[i]],
                                        [sc.volume[i], sc.mass[i], sc.pd_min[i], sc.pd_max[i], *sc.center[i], *sc.velocity[i]],
-                                       rtol=1e-11, atol=1e-14)
+                                       rtol=stat_tol, atol=1e-14)
     compare_states(gpu, cpu, tol)
     return gpu, cpu
 
@@ -78,11 +97,38 @@ def test_gpu_matches_oracle_and_reference_fixture(name):
     p, nsteps = cases.GOLDEN_CASES[name]
     if p["linear_solver_pressure"] == "lu_relaxed":
         pytest.skip("lu_relaxed is not on the GPU path yet (SURVEY 8f rank 4)")
-    gpu, cpu = run_both(p, nsteps)
+    # rt3d_8_jacobi_dtauto is an unstable flow (dt_auto lets dt jump): the 1-ulp difference between
+    # device and host sin() in the initial velocity is amplified ~1e7 times in 3 steps; its exactness is
+    # covered by test_gpu_bit_exact_from_identical_state instead
+    loose = name == "rt3d_8_jacobi_dtauto"
+    gpu, cpu = run_both(p, nsteps, tol=1e-6 if loose else TOL, stat_tol=1e-6 if loose else 1e-11)
     g = np.load(os.path.join(GOLD, "ref_%s.npz" % name))
     for fname, key in GOLD_KEYS.items():
         if key in g.files and has_field(cpu, fname):
-            assert rel_l2(gpu.get(fname), g[key]) <= 1e-11, (fname, rel_l2(gpu.get(fname), g[key]))
+            e = field_error(gpu, cpu, fname, ref=g[key])
+            assert e <= (1e-6 if loose else 1e-11), (fname, e)
+
+
+@pytest.mark.parametrize("name", ["rt3d_16", "dam3d_32x10x10", "thermal2d_32x16", "cavity_16", "rt3d_8_jacobi_dtauto",
+                                  "dam2d_36x20", "rt3d_12x10x9"])
+def test_gpu_bit_exact_from_identical_state(name):
+    """Started from bit-identical fields (the oracle's initial state uploaded through hg_set_field, which
+    removes the 1-ulp difference between device and host sin() in the initial velocity), the CUDA path
+    reproduces the oracle -- hence the reference -- to the last bit: same operation order, no FMA."""
+    from hydro_b200.capi import Hydro
+    p, nsteps = cases.GOLDEN_CASES[name]
+    gpu, cpu = Hydro(p), Oracle(p)
+    for f in ("VELOCITY_X", "VELOCITY_Y", "VELOCITY_Z", "VOLUME_FLUX", "PARTIAL_DENSITY_0", "PARTIAL_DENSITY_1"):
+        if has_field(cpu, f):
+            gpu.set(f, cpu.get(f))
+    gpu.update_properties()
+    for _ in range(nsteps):
+        gpu.step(), cpu.step()
+    for f in ("VELOCITY_X", "VELOCITY_Y", "VELOCITY_Z", "PRESSURE", "VOLUME_FLUX", "PARTIAL_DENSITY_0",
+              "PARTIAL_DENSITY_1", "TEMPERATURE", "DENSITY", "VISCOSITY"):
+        if has_field(cpu, f):
+            assert np.array_equal(gpu.get(f), cpu.get(f)), f
+    assert np.array_equal(gpu.residuals(), cpu.residuals())
 
 
 def test_gpu_cavity_sample_first_iterations():
@@ -197,7 +243,7 @@ def test_set_get_roundtrip_and_idempotent_properties():
     h = Hydro(cases.rt3d(8))
     for name in ("VELOCITY_X", "PRESSURE", "VOLUME_FLUX", "PARTIAL_DENSITY_1"):
         n = h.nf if F[name] == F["VOLUME_FLUX"] else h.nc
-        v = sin_field(n)
+        v = 0.6 + 0.3 * sin_field(n)
         h.set(name, v)
         assert np.array_equal(h.get(name), v)
     h.update_properties()
