@@ -20,30 +20,41 @@ constexpr int SOLVER_BX = 64;   // threads along i
 constexpr int SOLVER_BY = 4;    // rows (j) per tile
 constexpr int SOLVER_THREADS = SOLVER_BX * SOLVER_BY;
 
-struct PlaneTiling {
-  int rg;   // row groups per plane = ceil(ny / BY)
-  int ch;   // i-chunks per row group
-  int tiles;
+// Hyperplane tiles.  A tile is SOLVER_BY consecutive rows j x SOLVER_BX consecutive i of one plane
+// k' = i+j+k; only tiles that contain at least one cell are listed (built once per mesh on the host).
+struct TileTable {
+  const int* tile_j0;    // first row of the tile
+  const int* tile_i0;    // first i of the tile
+  const int* tileoff;    // [np+1] first tile of plane k'
+  const int* cum2;       // [np] tiles of planes k', k'-2, k'-4, ... (same-parity running sum)
 };
-__host__ __device__ inline PlaneTiling plane_tiling(const Geo& g) {
-  PlaneTiling t;
-  t.rg = (g.n[1] + SOLVER_BY - 1) / SOLVER_BY;
-  int width = g.n[2] + SOLVER_BY - 1;              // i-extent of the valid band over BY rows
-  if (width > g.n[0]) width = g.n[0];
-  t.ch = (width + SOLVER_BX - 1) / SOLVER_BX;
-  t.tiles = t.rg * t.ch;
-  return t;
-}
-// cell handled by this thread for tile `local` of plane kp; returns false if none
-DV bool tile_cell(const Geo& g, const PlaneTiling& pt, int kp, int local, int& i, int& j, int& k) {
-  const int rgi = local / pt.ch, chi = local % pt.ch;
-  const int j0 = rgi * SOLVER_BY;
-  int ilo = kp - (j0 + SOLVER_BY - 1) - (g.n[2] - 1);
-  if (ilo < 0) ilo = 0;
-  j = j0 + (threadIdx.x / SOLVER_BX);
-  i = ilo + chi * SOLVER_BX + (threadIdx.x % SOLVER_BX);
+// cell handled by this thread in tile e of plane kp
+DV bool tile_cell(const Geo& g, const TileTable& tt, int e, int kp, int& i, int& j, int& k) {
+  j = tt.tile_j0[e] + (threadIdx.x / SOLVER_BX);
+  i = tt.tile_i0[e] + (threadIdx.x % SOLVER_BX);
   k = kp - i - j;
   return j < g.n[1] && i < g.n[0] && k >= 0 && k < g.n[2];
+}
+// Tiles of step T for sweeps [smin, smax] (planes T-2s): flat id -> (plane, tile) by binary search in cum2
+struct StepTiles { int kp_lo, kp_hi, base, total; };
+DV StepTiles step_tiles(const Geo& g, const TileTable& tt, int T, int S) {
+  int smin = 0; if (T - (g.np - 1) > 0) smin = (T - (g.np - 1) + 1) / 2;
+  int smax = T / 2; if (smax > S - 1) smax = S - 1;
+  StepTiles st;
+  st.kp_hi = T - 2 * smin; st.kp_lo = T - 2 * smax;
+  st.base = st.kp_lo >= 2 ? tt.cum2[st.kp_lo - 2] : 0;
+  st.total = smax >= smin ? tt.cum2[st.kp_hi] - st.base : 0;
+  return st;
+}
+DV void locate_tile(const TileTable& tt, const StepTiles& st, int id, int& kp, int& e) {
+  const int target = st.base + id;
+  int lo = 0, hi = (st.kp_hi - st.kp_lo) >> 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (tt.cum2[st.kp_lo + 2 * mid] > target) hi = mid; else lo = mid + 1;
+  }
+  kp = st.kp_lo + 2 * lo;
+  e = tt.tileoff[kp] + target - (kp >= 2 ? tt.cum2[kp - 2] : 0);
 }
 
 // ---------------------------------------------------------------- pressure: Gauss-Seidel / SOR
@@ -54,75 +65,76 @@ struct GsArgs {
   double* diff;        // per-sweep max |value - x| (linear.hpp:707), indexed by absolute sweep number
   int s_begin, s_end;  // sweeps [s_begin, s_end) are run by this launch
   double omega;
+  TileTable tt;
 };
 
-// off-diagonal coupling c_f = A/(h d_f) toward neighbour (ni,nj,nk) through face direction d; 0 when
-// the face is not an inner face or either cell is the fixed-pressure cell (fluid.hpp:997-1014)
-template <int DIM>
-DV double gs_coeff(const Geo& g, const double* __restrict__ D, double d0, int d, int ni, int nj, int nk, bool& inner) {
-  inner = cell_ok(g, ni, nj, nk);
-  if (!inner) return 0.;
-  const double dn = D[shidx(g, ni, nj, nk)];
-  // d_f = d[cm]*0.5 + d[cp]*0.5 (commutative), coeff = -A/(h d_f), c_f = -coeff
+// off-diagonal coupling c_f = A/(h d_f) through a face of direction d between this cell (d0) and a
+// neighbour with diagonal value dn (fluid.hpp:957-964): d_f = d[cm]*0.5 + d[cp]*0.5, coeff = -A/(h d_f)
+DV double gs_cf(const Geo& g, int d, double dn, double d0) {
   const double dfc = dn * (1. - 0.5) + d0 * 0.5;
   const double coeff = -g.area[d] / (g.h[d] * dfc);
   return -coeff;
 }
 
-template <int DIM>
-__global__ void __launch_bounds__(SOLVER_THREADS) k_gs_persistent(Geo g, GsArgs a) {
+template <int DIM, bool EXCL>
+__global__ void __launch_bounds__(SOLVER_THREADS, 4) k_gs_persistent(Geo g, GsArgs a) {
   cg::grid_group grid = cg::this_grid();
-  const PlaneTiling pt = plane_tiling(g);
   const int S = a.s_end - a.s_begin;
   const int Tmax = (g.np - 1) + 2 * (S - 1);
-  __shared__ double sm[SOLVER_THREADS / 32];
+  const long long PS = (long long)g.n[1] * g.n[0];   // plane stride of the sheared layout
+  const int nx = g.n[0];
   for (int T = 0; T <= Tmax; ++T) {
-    // sweeps (relative) with 0 <= T - 2 s <= np-1
-    int smin = (T - (g.np - 1) + 1) / 2; if (T - (g.np - 1) <= 0) smin = 0;
-    int smax = T / 2; if (smax > S - 1) smax = S - 1;
-    const int nact = smax - smin + 1;
-    const long long ntiles = (long long)nact * pt.tiles;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int s = smin + (int)(tile / pt.tiles);
-      const int local = (int)(tile % pt.tiles);
-      const int kp = T - 2 * s;
+    const StepTiles st = step_tiles(g, a.tt, T, S);
+    for (int id = blockIdx.x; id < st.total; id += gridDim.x) {
+      int kp, e; locate_tile(a.tt, st, id, kp, e);
+      const int s = (T - kp) >> 1;
       int i, j, k;
       double ac = 0.;
-      if (tile_cell(g, pt, kp, local, i, j, k)) {
-        const long long cs = shidx(g, i, j, k);
+      if (tile_cell(g, a.tt, e, kp, i, j, k)) {
+        const long long cs = ((long long)kp * g.n[1] + j) * nx + i;
+        const long long c = i + g.sy * j + g.sz * k;
+        // neighbours in the sheared layout: x-: cs-PS-1, y-: cs-PS-nx, z-: cs-PS, x+: cs+PS+1, y+: cs+PS+nx, z+: cs+PS
+        bool in_xm = i > 0, in_xp = i + 1 < nx, in_ym = j > 0, in_yp = j + 1 < g.n[1];
+        bool in_zm = DIM > 2 && k > 0, in_zp = DIM > 2 && k + 1 < g.n[2];
+        bool ident = c == g.pfix;
+        if (EXCL) {
+          ident = ident || g.excl[c] != 0;
+          in_xm = in_xm && g.excl[c - 1] == 0; in_xp = in_xp && g.excl[c + 1] == 0;
+          in_ym = in_ym && g.excl[c - g.sy] == 0; in_yp = in_yp && g.excl[c + g.sy] == 0;
+          if (DIM > 2) { in_zm = in_zm && g.excl[c - g.sz] == 0; in_zp = in_zp && g.excl[c + g.sz] == 0; }
+        }
         const double rhs = a.RP[cs];
         const double xold = __ldcg(&a.PP[cs]);
-        double diag, sum = 0.;
-        const bool ident = cell_excl(g, i, j, k) || cidx(g, i, j, k) == g.pfix;
-        if (ident) { diag = 1.; }
-        else {
-          const double d0 = a.D[cs];
-          bool in_xm, in_xp, in_ym, in_yp, in_zm = false, in_zp = false;
-          const double cxm = gs_coeff<DIM>(g, a.D, d0, 0, i - 1, j, k, in_xm);
-          const double cxp = gs_coeff<DIM>(g, a.D, d0, 0, i + 1, j, k, in_xp);
-          const double cym = gs_coeff<DIM>(g, a.D, d0, 1, i, j - 1, k, in_ym);
-          const double cyp = gs_coeff<DIM>(g, a.D, d0, 1, i, j + 1, k, in_yp);
-          double czm = 0., czp = 0.;
-          if (DIM > 2) { czm = gs_coeff<DIM>(g, a.D, d0, 2, i, j, k - 1, in_zm); czp = gs_coeff<DIM>(g, a.D, d0, 2, i, j, k + 1, in_zp); }
+        const double d0 = a.D[cs];
+        // issue all neighbour loads up front (independent addresses)
+        const double dxm = in_xm ? a.D[cs - PS - 1] : 1., dxp = in_xp ? a.D[cs + PS + 1] : 1.;
+        const double dym = in_ym ? a.D[cs - PS - nx] : 1., dyp = in_yp ? a.D[cs + PS + nx] : 1.;
+        const double dzm = in_zm ? a.D[cs - PS] : 1., dzp = in_zp ? a.D[cs + PS] : 1.;
+        const double pxm = in_xm ? __ldcg(&a.PP[cs - PS - 1]) : 0., pxp = in_xp ? __ldcg(&a.PP[cs + PS + 1]) : 0.;
+        const double pym = in_ym ? __ldcg(&a.PP[cs - PS - nx]) : 0., pyp = in_yp ? __ldcg(&a.PP[cs + PS + nx]) : 0.;
+        const double pzm = in_zm ? __ldcg(&a.PP[cs - PS]) : 0., pzp = in_zp ? __ldcg(&a.PP[cs + PS]) : 0.;
+        double diag = 1., sum = 0.;
+        if (!ident) {
+          const double cxm = gs_cf(g, 0, dxm, d0), cxp = gs_cf(g, 0, dxp, d0);
+          const double cym = gs_cf(g, 1, dym, d0), cyp = gs_cf(g, 1, dyp, d0);
+          const double czm = DIM > 2 ? gs_cf(g, 2, dzm, d0) : 0., czp = DIM > 2 ? gs_cf(g, 2, dzp, d0) : 0.;
           // diagonal: contributions merged in face order x-,x+,y-,y+,z-,z+ (fluid.hpp:979-984)
           bool have = false; diag = 0.;
           if (in_xm) { diag = have ? diag + cxm : cxm; have = true; }
           if (in_xp) { diag = have ? diag + cxp : cxp; have = true; }
           if (in_ym) { diag = have ? diag + cym : cym; have = true; }
           if (in_yp) { diag = have ? diag + cyp : cyp; have = true; }
-          if (DIM > 2) {
-            if (in_zm) { diag = have ? diag + czm : czm; have = true; }
-            if (in_zp) { diag = have ? diag + czp : czp; have = true; }
-          }
+          if (in_zm) { diag = have ? diag + czm : czm; have = true; }
+          if (in_zp) { diag = have ? diag + czp : czp; have = true; }
           // off-diagonal terms in ascending index order z-,y-,x-,x+,y+,z+ (linear.hpp:694-701);
-          // terms toward the fixed-pressure cell were removed by SetKnownValue
+          // terms toward the fixed-pressure cell were removed by SetKnownValue (fluid.hpp:1010)
           const long long pf = g.pfix;
-          if (DIM > 2 && in_zm && cidx(g, i, j, k - 1) != pf) sum += (-czm) * __ldcg(&a.PP[shidx(g, i, j, k - 1)]);
-          if (in_ym && cidx(g, i, j - 1, k) != pf) sum += (-cym) * __ldcg(&a.PP[shidx(g, i, j - 1, k)]);
-          if (in_xm && cidx(g, i - 1, j, k) != pf) sum += (-cxm) * __ldcg(&a.PP[shidx(g, i - 1, j, k)]);
-          if (in_xp && cidx(g, i + 1, j, k) != pf) sum += (-cxp) * __ldcg(&a.PP[shidx(g, i + 1, j, k)]);
-          if (in_yp && cidx(g, i, j + 1, k) != pf) sum += (-cyp) * __ldcg(&a.PP[shidx(g, i, j + 1, k)]);
-          if (DIM > 2 && in_zp && cidx(g, i, j, k + 1) != pf) sum += (-czp) * __ldcg(&a.PP[shidx(g, i, j, k + 1)]);
+          if (in_zm && c - g.sz != pf) sum += (-czm) * pzm;
+          if (in_ym && c - g.sy != pf) sum += (-cym) * pym;
+          if (in_xm && c - 1 != pf) sum += (-cxm) * pxm;
+          if (in_xp && c + 1 != pf) sum += (-cxp) * pxp;
+          if (in_yp && c + g.sy != pf) sum += (-cyp) * pyp;
+          if (in_zp && c + g.sz != pf) sum += (-czp) * pzp;
         }
         const double value = -(rhs + sum) / diag;
         const double corr = value - xold;
@@ -130,16 +142,9 @@ __global__ void __launch_bounds__(SOLVER_THREADS) k_gs_persistent(Geo g, GsArgs 
         ac = fabs(corr);
         if (!(ac == ac)) ac = 0.;
       }
-      // per-sweep max-norm (linear.hpp:707)
+      // per-sweep max-norm (linear.hpp:707): one reduction atomic per warp
       ac = warp_max(ac);
-      if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = ac;
-      __syncthreads();
-      if (threadIdx.x < 32) {
-        double v = threadIdx.x < SOLVER_THREADS / 32 ? sm[threadIdx.x] : 0.;
-        v = warp_max(v);
-        if (threadIdx.x == 0 && v > 0.) atomic_max_nonneg(&a.diff[a.s_begin + s], v);
-      }
-      __syncthreads();
+      if ((threadIdx.x & 31) == 0 && ac > 0.) atomic_max_nonneg(&a.diff[a.s_begin + s], ac);
     }
     grid.sync();
   }
@@ -151,26 +156,27 @@ struct LuArgs {
   const double* R[3];   // sheared constants
   double* X[3];         // sheared result
   int ncomp;
+  TileTable tt;
 };
 template <int DIM>
-__global__ void __launch_bounds__(SOLVER_THREADS) k_lu_persistent(Geo g, LuArgs a) {
+__global__ void __launch_bounds__(SOLVER_THREADS, 4) k_lu_persistent(Geo g, LuArgs a) {
   cg::grid_group grid = cg::this_grid();
-  const PlaneTiling pt = plane_tiling(g);
+  const long long PS = (long long)g.n[1] * g.n[0];
+  const int nx = g.n[0];
   // forward step (linear.hpp:537-548)
   for (int kp = 0; kp < g.np; ++kp) {
-    for (int local = blockIdx.x; local < pt.tiles; local += gridDim.x) {
+    for (int e = a.tt.tileoff[kp] + blockIdx.x; e < a.tt.tileoff[kp + 1]; e += gridDim.x) {
       int i, j, k;
-      if (!tile_cell(g, pt, kp, local, i, j, k)) continue;
-      const long long cs = shidx(g, i, j, k);
+      if (!tile_cell(g, a.tt, e, kp, i, j, k)) continue;
+      const long long cs = ((long long)kp * g.n[1] + j) * nx + i;
       const bool zm = DIM > 2 && k > 0, ym = j > 0, xm = i > 0;
       const double azm = zm ? a.A[CZM][cs] : 0., aym = ym ? a.A[CYM][cs] : 0., axm = xm ? a.A[CXM][cs] : 0.;
       const double diag = a.A[CD][cs];
-      const long long nzm = zm ? shidx(g, i, j, k - 1) : 0, nym = ym ? shidx(g, i, j - 1, k) : 0, nxm = xm ? shidx(g, i - 1, j, k) : 0;
       for (int n = 0; n < a.ncomp; ++n) {
         double sum = 0.;
-        if (zm) sum += azm * __ldcg(&a.X[n][nzm]);
-        if (ym) sum += aym * __ldcg(&a.X[n][nym]);
-        if (xm) sum += axm * __ldcg(&a.X[n][nxm]);
+        if (zm) sum += azm * __ldcg(&a.X[n][cs - PS]);
+        if (ym) sum += aym * __ldcg(&a.X[n][cs - PS - nx]);
+        if (xm) sum += axm * __ldcg(&a.X[n][cs - PS - 1]);
         a.X[n][cs] = (-a.R[n][cs] - sum) / diag;
       }
     }
@@ -178,19 +184,18 @@ __global__ void __launch_bounds__(SOLVER_THREADS) k_lu_persistent(Geo g, LuArgs 
   }
   // backward step (linear.hpp:551-563)
   for (int kp = g.np - 1; kp >= 0; --kp) {
-    for (int local = blockIdx.x; local < pt.tiles; local += gridDim.x) {
+    for (int e = a.tt.tileoff[kp] + blockIdx.x; e < a.tt.tileoff[kp + 1]; e += gridDim.x) {
       int i, j, k;
-      if (!tile_cell(g, pt, kp, local, i, j, k)) continue;
-      const long long cs = shidx(g, i, j, k);
-      const bool zp = DIM > 2 && k + 1 < g.n[2], yp = j + 1 < g.n[1], xp = i + 1 < g.n[0];
+      if (!tile_cell(g, a.tt, e, kp, i, j, k)) continue;
+      const long long cs = ((long long)kp * g.n[1] + j) * nx + i;
+      const bool zp = DIM > 2 && k + 1 < g.n[2], yp = j + 1 < g.n[1], xp = i + 1 < nx;
       const double azp = zp ? a.A[CZP][cs] : 0., ayp = yp ? a.A[CYP][cs] : 0., axp = xp ? a.A[CXP][cs] : 0.;
       const double diag = a.A[CD][cs];
-      const long long nzp = zp ? shidx(g, i, j, k + 1) : 0, nyp = yp ? shidx(g, i, j + 1, k) : 0, nxp = xp ? shidx(g, i + 1, j, k) : 0;
       for (int n = 0; n < a.ncomp; ++n) {
         double sum = 0.;
-        if (zp) sum += azp * __ldcg(&a.X[n][nzp]);
-        if (yp) sum += ayp * __ldcg(&a.X[n][nyp]);
-        if (xp) sum += axp * __ldcg(&a.X[n][nxp]);
+        if (zp) sum += azp * __ldcg(&a.X[n][cs + PS]);
+        if (yp) sum += ayp * __ldcg(&a.X[n][cs + PS + nx]);
+        if (xp) sum += axp * __ldcg(&a.X[n][cs + PS + 1]);
         a.X[n][cs] = __ldcg(&a.X[n][cs]) - sum / diag;
       }
     }
@@ -201,34 +206,31 @@ __global__ void __launch_bounds__(SOLVER_THREADS) k_lu_persistent(Geo g, LuArgs 
 // ---------------------------------------------------------------- generic-matrix sweeps (hg_linear_solve and
 // pressure systems given explicitly): SOR with stored rows, same pipelining as k_gs_persistent
 struct SorArgs {
-  const double* A[7]; const double* R; double* X; double* diff; int s_begin, s_end; double omega;
+  const double* A[7]; const double* R; double* X; double* diff; int s_begin, s_end; double omega; TileTable tt;
 };
 template <int DIM>
-__global__ void __launch_bounds__(SOLVER_THREADS) k_sor_matrix_persistent(Geo g, SorArgs a) {
+__global__ void __launch_bounds__(SOLVER_THREADS, 4) k_sor_matrix_persistent(Geo g, SorArgs a) {
   cg::grid_group grid = cg::this_grid();
-  const PlaneTiling pt = plane_tiling(g);
   const int S = a.s_end - a.s_begin;
   const int Tmax = (g.np - 1) + 2 * (S - 1);
-  __shared__ double sm[SOLVER_THREADS / 32];
+  const long long PS = (long long)g.n[1] * g.n[0];
+  const int nx = g.n[0];
   for (int T = 0; T <= Tmax; ++T) {
-    int smin = (T - (g.np - 1) + 1) / 2; if (T - (g.np - 1) <= 0) smin = 0;
-    int smax = T / 2; if (smax > S - 1) smax = S - 1;
-    const long long ntiles = (long long)(smax - smin + 1) * pt.tiles;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int s = smin + (int)(tile / pt.tiles);
-      const int local = (int)(tile % pt.tiles);
-      const int kp = T - 2 * s;
+    const StepTiles st = step_tiles(g, a.tt, T, S);
+    for (int id = blockIdx.x; id < st.total; id += gridDim.x) {
+      int kp, e; locate_tile(a.tt, st, id, kp, e);
+      const int s = (T - kp) >> 1;
       int i, j, k;
       double ac = 0.;
-      if (tile_cell(g, pt, kp, local, i, j, k)) {
-        const long long cs = shidx(g, i, j, k);
+      if (tile_cell(g, a.tt, e, kp, i, j, k)) {
+        const long long cs = ((long long)kp * g.n[1] + j) * nx + i;
         double sum = 0.;
-        if (DIM > 2 && k > 0) sum += a.A[CZM][cs] * __ldcg(&a.X[shidx(g, i, j, k - 1)]);
-        if (j > 0) sum += a.A[CYM][cs] * __ldcg(&a.X[shidx(g, i, j - 1, k)]);
-        if (i > 0) sum += a.A[CXM][cs] * __ldcg(&a.X[shidx(g, i - 1, j, k)]);
-        if (i + 1 < g.n[0]) sum += a.A[CXP][cs] * __ldcg(&a.X[shidx(g, i + 1, j, k)]);
-        if (j + 1 < g.n[1]) sum += a.A[CYP][cs] * __ldcg(&a.X[shidx(g, i, j + 1, k)]);
-        if (DIM > 2 && k + 1 < g.n[2]) sum += a.A[CZP][cs] * __ldcg(&a.X[shidx(g, i, j, k + 1)]);
+        if (DIM > 2 && k > 0) sum += a.A[CZM][cs] * __ldcg(&a.X[cs - PS]);
+        if (j > 0) sum += a.A[CYM][cs] * __ldcg(&a.X[cs - PS - nx]);
+        if (i > 0) sum += a.A[CXM][cs] * __ldcg(&a.X[cs - PS - 1]);
+        if (i + 1 < nx) sum += a.A[CXP][cs] * __ldcg(&a.X[cs + PS + 1]);
+        if (j + 1 < g.n[1]) sum += a.A[CYP][cs] * __ldcg(&a.X[cs + PS + nx]);
+        if (DIM > 2 && k + 1 < g.n[2]) sum += a.A[CZP][cs] * __ldcg(&a.X[cs + PS]);
         const double xold = __ldcg(&a.X[cs]);
         const double value = -(a.R[cs] + sum) / a.A[CD][cs];
         const double corr = value - xold;
@@ -237,14 +239,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS) k_sor_matrix_persistent(Geo g,
         if (!(ac == ac)) ac = 0.;
       }
       ac = warp_max(ac);
-      if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = ac;
-      __syncthreads();
-      if (threadIdx.x < 32) {
-        double v = threadIdx.x < SOLVER_THREADS / 32 ? sm[threadIdx.x] : 0.;
-        v = warp_max(v);
-        if (threadIdx.x == 0 && v > 0.) atomic_max_nonneg(&a.diff[a.s_begin + s], v);
-      }
-      __syncthreads();
+      if ((threadIdx.x & 31) == 0 && ac > 0.) atomic_max_nonneg(&a.diff[a.s_begin + s], ac);
     }
     grid.sync();
   }

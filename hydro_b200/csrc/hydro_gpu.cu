@@ -51,6 +51,7 @@ struct hg_state {
   hg_step_stats stat;
   long long launches = 0;
   int grid_solver = 0, grid_lu = 0;
+  TileTable tt;
   bool timers_on = false;
   std::map<std::string, Timer> timers;
   std::vector<std::string> timer_stack;
@@ -253,9 +254,11 @@ static int solve_pressure(hg_state* s) {
   if (c.linear_solver_pressure == HG_LS_GAUSS_SEIDEL) {
     auto launch = [&](int sb, int se) -> int {
       GsArgs a; a.D = s->D; a.RP = s->RP; a.PP = s->PP; a.diff = s->diffs; a.s_begin = sb; a.s_end = se;
-      a.omega = c.lu_relaxed_relaxation_factor;
-      if (s->dim == 3) return coop_launch(s, k_gs_persistent<3>, s->grid_solver, s->geo, a, 0);
-      return coop_launch(s, k_gs_persistent<2>, s->grid_solver, s->geo, a, 0);
+      a.omega = c.lu_relaxed_relaxation_factor; a.tt = s->tt;
+      if (s->dim == 3) return s->any_excl ? coop_launch(s, k_gs_persistent<3, true>, s->grid_solver, s->geo, a, 0)
+                                          : coop_launch(s, k_gs_persistent<3, false>, s->grid_solver, s->geo, a, 0);
+      return s->any_excl ? coop_launch(s, k_gs_persistent<2, true>, s->grid_solver, s->geo, a, 0)
+                         : coop_launch(s, k_gs_persistent<2, false>, s->grid_solver, s->geo, a, 0);
     };
     if (int rc = run_sor(s, s->PP, s->nsh, c.lu_relaxed_tolerance, c.lu_relaxed_num_iters_limit, launch, &it, &df)) return rc;
     DIMSEL(s, k_pcorr, nblk(s->nc), 256, s->geo, s->PP, s->p[L_IP], c.pressure_relaxation_factor, s->pc, s->p[L_IC]);
@@ -279,7 +282,7 @@ static int solve_lu(hg_state* s, int ncomp) {
   LuArgs a;
   for (int t = 0; t < 7; ++t) a.A[t] = s->A[t];
   for (int n = 0; n < 3; ++n) { a.R[n] = s->R[n]; a.X[n] = s->X[n]; }
-  a.ncomp = ncomp;
+  a.ncomp = ncomp; a.tt = s->tt;
   if (s->dim == 3) return coop_launch(s, k_lu_persistent<3>, s->grid_lu, s->geo, a, 1);
   return coop_launch(s, k_lu_persistent<2>, s->grid_lu, s->geo, a, 1);
 }
@@ -737,16 +740,43 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
   cudaDeviceProp prop; cudaGetDeviceProperties(&prop, s->dev);
   int occ_gs = 0, occ_lu = 0;
   if (dim == 3) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gs, k_gs_persistent<3>, SOLVER_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gs, k_gs_persistent<3, true>, SOLVER_THREADS, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lu, k_lu_persistent<3>, SOLVER_THREADS, 0);
   } else {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gs, k_gs_persistent<2>, SOLVER_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gs, k_gs_persistent<2, true>, SOLVER_THREADS, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lu, k_lu_persistent<2>, SOLVER_THREADS, 0);
   }
   if (occ_gs < 1 || occ_lu < 1) return fail_create(s, HG_ERR_CUDA, "solver kernel does not fit on an SM");
-  s->grid_solver = prop.multiProcessorCount * std::min(occ_gs, 4);
+  s->grid_solver = prop.multiProcessorCount * std::min(occ_gs, 8);
   s->grid_lu = prop.multiProcessorCount * std::min(occ_lu, 2);
 
+  // hyperplane tile table for the ordered sweeps (hg_solvers.cuh)
+  {
+    std::vector<int> tj, ti, toff(g.np + 1, 0), cum2(g.np, 0);
+    const int nx = s->n[0], ny = s->n[1], nz = s->n[2];
+    for (int kp = 0; kp < g.np; ++kp) {
+      toff[kp] = (int)tj.size();
+      for (int j0 = 0; j0 < ny; j0 += SOLVER_BY) {
+        if (j0 > kp) break;
+        const int j1 = std::min(j0 + SOLVER_BY - 1, ny - 1);
+        const int ihi = std::min(nx - 1, kp - j0);             // largest valid i over the rows
+        const int ilo = std::max(0, kp - j1 - (nz - 1));       // smallest valid i over the rows
+        if (ilo > ihi) continue;
+        for (int i0 = ilo; i0 <= ihi; i0 += SOLVER_BX) { tj.push_back(j0); ti.push_back(i0); }
+      }
+    }
+    toff[g.np] = (int)tj.size();
+    for (int kp = 0; kp < g.np; ++kp) cum2[kp] = (toff[kp + 1] - toff[kp]) + (kp >= 2 ? cum2[kp - 2] : 0);
+    int *d_tj = nullptr, *d_ti = nullptr, *d_off = nullptr, *d_c2 = nullptr;
+    if (dalloc(s, &d_tj, (long long)tj.size(), false) || dalloc(s, &d_ti, (long long)ti.size(), false) ||
+        dalloc(s, &d_off, g.np + 1, false) || dalloc(s, &d_c2, g.np, false))
+      return fail_create(s, HG_ERR_CUDA, "allocation failed: " + s->err);
+    cudaMemcpy(d_tj, tj.data(), tj.size() * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_ti, ti.data(), ti.size() * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_off, toff.data(), toff.size() * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_c2, cum2.data(), cum2.size() * sizeof(int), cudaMemcpyHostToDevice);
+    s->tt.tile_j0 = d_tj; s->tt.tile_i0 = d_ti; s->tt.tileoff = d_off; s->tt.cum2 = d_c2;
+  }
   // rigid box -> excluded cells (hydro2d.hpp:409-416)
   {
     int* anyflag = s->flag + 1;
@@ -940,7 +970,7 @@ extern "C" int hg_linear_solve(hg_handle s, int solver, const double* const coef
   } else if (solver == HG_LS_GAUSS_SEIDEL) {
     auto launch = [&](int sb, int se) -> int {
       SorArgs a; for (int t = 0; t < 7; ++t) a.A[t] = s->A[t];
-      a.R = s->R[0]; a.X = s->PP; a.diff = s->diffs; a.s_begin = sb; a.s_end = se; a.omega = relax;
+      a.R = s->R[0]; a.X = s->PP; a.diff = s->diffs; a.s_begin = sb; a.s_end = se; a.omega = relax; a.tt = s->tt;
       if (s->dim == 3) return coop_launch(s, k_sor_matrix_persistent<3>, s->grid_solver, s->geo, a);
       return coop_launch(s, k_sor_matrix_persistent<2>, s->grid_solver, s->geo, a);
     };
