@@ -18,7 +18,10 @@ namespace cg = cooperative_groups;
 
 constexpr int SOLVER_BX = 64;   // threads along i
 constexpr int SOLVER_BY = 4;    // rows (j) per tile
-constexpr int SOLVER_THREADS = SOLVER_BX * SOLVER_BY;
+constexpr int SOLVER_TILE = SOLVER_BX * SOLVER_BY;   // cells per tile = threads per tile slot
+constexpr int SOLVER_SLOTS = 4;                       // tile slots per CTA
+constexpr int SOLVER_THREADS = SOLVER_TILE * SOLVER_SLOTS;   // 1024: one CTA per SM, 148 CTAs -> cheap grid barrier
+constexpr int SOLVER_SC = 1024;                       // max sweeps in flight per launch (shared table)
 
 // Hyperplane tiles.  A tile is SOLVER_BY consecutive rows j x SOLVER_BX consecutive i of one plane
 // k' = i+j+k; only tiles that contain at least one cell are listed (built once per mesh on the host).
@@ -30,8 +33,9 @@ struct TileTable {
 };
 // cell handled by this thread in tile e of plane kp
 DV bool tile_cell(const Geo& g, const TileTable& tt, int e, int kp, int& i, int& j, int& k) {
-  j = tt.tile_j0[e] + (threadIdx.x / SOLVER_BX);
-  i = tt.tile_i0[e] + (threadIdx.x % SOLVER_BX);
+  const int lt = threadIdx.x & (SOLVER_TILE - 1);
+  j = tt.tile_j0[e] + (lt / SOLVER_BX);
+  i = tt.tile_i0[e] + (lt % SOLVER_BX);
   k = kp - i - j;
   return j < g.n[1] && i < g.n[0] && k >= 0 && k < g.n[2];
 }
@@ -46,15 +50,12 @@ DV StepTiles step_tiles(const Geo& g, const TileTable& tt, int T, int S) {
   st.total = smax >= smin ? tt.cum2[st.kp_hi] - st.base : 0;
   return st;
 }
-DV void locate_tile(const TileTable& tt, const StepTiles& st, int id, int& kp, int& e) {
-  const int target = st.base + id;
-  int lo = 0, hi = (st.kp_hi - st.kp_lo) >> 1;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (tt.cum2[st.kp_lo + 2 * mid] > target) hi = mid; else lo = mid + 1;
-  }
-  kp = st.kp_lo + 2 * lo;
-  e = tt.tileoff[kp] + target - (kp >= 2 ? tt.cum2[kp - 2] : 0);
+// Per step: sc[m] = number of tiles of the m+1 lowest active planes (inclusive running count), kept in
+// shared memory; a slot walks its ids in ascending order, so (plane, tile) follow by a two-pointer scan.
+DV void fill_step_table(const TileTable& tt, const StepTiles& st, int* sc) {
+  const int nact = ((st.kp_hi - st.kp_lo) >> 1) + 1;
+  for (int t = threadIdx.x; t < nact; t += blockDim.x) sc[t] = tt.cum2[st.kp_lo + 2 * t] - st.base;
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------- pressure: Gauss-Seidel / SOR
@@ -77,16 +78,22 @@ DV double gs_cf(const Geo& g, int d, double dn, double d0) {
 }
 
 template <int DIM, bool EXCL>
-__global__ void __launch_bounds__(SOLVER_THREADS, 4) k_gs_persistent(Geo g, GsArgs a) {
+__global__ void __launch_bounds__(SOLVER_THREADS, 1) k_gs_persistent(Geo g, GsArgs a) {
   cg::grid_group grid = cg::this_grid();
+  __shared__ int sc[SOLVER_SC];
   const int S = a.s_end - a.s_begin;
   const int Tmax = (g.np - 1) + 2 * (S - 1);
   const long long PS = (long long)g.n[1] * g.n[0];   // plane stride of the sheared layout
   const int nx = g.n[0];
+  const int gslot = blockIdx.x * SOLVER_SLOTS + (threadIdx.x / SOLVER_TILE), nslots = gridDim.x * SOLVER_SLOTS;
   for (int T = 0; T <= Tmax; ++T) {
     const StepTiles st = step_tiles(g, a.tt, T, S);
-    for (int id = blockIdx.x; id < st.total; id += gridDim.x) {
-      int kp, e; locate_tile(a.tt, st, id, kp, e);
+    fill_step_table(a.tt, st, sc);
+    int m = 0;
+    for (int id = gslot; id < st.total; id += nslots) {
+      while (sc[m] <= id) ++m;
+      const int kp = st.kp_lo + 2 * m;
+      const int e = a.tt.tileoff[kp] + id - (m > 0 ? sc[m - 1] : 0);
       const int s = (T - kp) >> 1;
       int i, j, k;
       double ac = 0.;
@@ -159,13 +166,14 @@ struct LuArgs {
   TileTable tt;
 };
 template <int DIM>
-__global__ void __launch_bounds__(SOLVER_THREADS, 4) k_lu_persistent(Geo g, LuArgs a) {
+__global__ void __launch_bounds__(SOLVER_THREADS, 1) k_lu_persistent(Geo g, LuArgs a) {
   cg::grid_group grid = cg::this_grid();
   const long long PS = (long long)g.n[1] * g.n[0];
   const int nx = g.n[0];
+  const int gslot = blockIdx.x * SOLVER_SLOTS + (threadIdx.x / SOLVER_TILE), nslots = gridDim.x * SOLVER_SLOTS;
   // forward step (linear.hpp:537-548)
   for (int kp = 0; kp < g.np; ++kp) {
-    for (int e = a.tt.tileoff[kp] + blockIdx.x; e < a.tt.tileoff[kp + 1]; e += gridDim.x) {
+    for (int e = a.tt.tileoff[kp] + gslot; e < a.tt.tileoff[kp + 1]; e += nslots) {
       int i, j, k;
       if (!tile_cell(g, a.tt, e, kp, i, j, k)) continue;
       const long long cs = ((long long)kp * g.n[1] + j) * nx + i;
@@ -184,7 +192,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 4) k_lu_persistent(Geo g, LuAr
   }
   // backward step (linear.hpp:551-563)
   for (int kp = g.np - 1; kp >= 0; --kp) {
-    for (int e = a.tt.tileoff[kp] + blockIdx.x; e < a.tt.tileoff[kp + 1]; e += gridDim.x) {
+    for (int e = a.tt.tileoff[kp] + gslot; e < a.tt.tileoff[kp + 1]; e += nslots) {
       int i, j, k;
       if (!tile_cell(g, a.tt, e, kp, i, j, k)) continue;
       const long long cs = ((long long)kp * g.n[1] + j) * nx + i;
@@ -209,16 +217,22 @@ struct SorArgs {
   const double* A[7]; const double* R; double* X; double* diff; int s_begin, s_end; double omega; TileTable tt;
 };
 template <int DIM>
-__global__ void __launch_bounds__(SOLVER_THREADS, 4) k_sor_matrix_persistent(Geo g, SorArgs a) {
+__global__ void __launch_bounds__(SOLVER_THREADS, 1) k_sor_matrix_persistent(Geo g, SorArgs a) {
   cg::grid_group grid = cg::this_grid();
+  __shared__ int sc[SOLVER_SC];
   const int S = a.s_end - a.s_begin;
   const int Tmax = (g.np - 1) + 2 * (S - 1);
   const long long PS = (long long)g.n[1] * g.n[0];
   const int nx = g.n[0];
+  const int gslot = blockIdx.x * SOLVER_SLOTS + (threadIdx.x / SOLVER_TILE), nslots = gridDim.x * SOLVER_SLOTS;
   for (int T = 0; T <= Tmax; ++T) {
     const StepTiles st = step_tiles(g, a.tt, T, S);
-    for (int id = blockIdx.x; id < st.total; id += gridDim.x) {
-      int kp, e; locate_tile(a.tt, st, id, kp, e);
+    fill_step_table(a.tt, st, sc);
+    int m = 0;
+    for (int id = gslot; id < st.total; id += nslots) {
+      while (sc[m] <= id) ++m;
+      const int kp = st.kp_lo + 2 * m;
+      const int e = a.tt.tileoff[kp] + id - (m > 0 ? sc[m - 1] : 0);
       const int s = (T - kp) >> 1;
       int i, j, k;
       double ac = 0.;

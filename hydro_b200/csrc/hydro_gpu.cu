@@ -162,7 +162,7 @@ static int run_sor(hg_state* s, double* x, long long nx_, double tol, int limit,
   CK(cudaMemsetAsync(s->diffs, 0, max_total * sizeof(double), s->st));
   if (!(tol > 0.)) {
     // `diff > tol` only fails for diff == 0 (or NaN): run all limit+1 sweeps, inspect the history once
-    if (int rc = launch(0, max_total)) return rc;
+    for (int sb = 0; sb < max_total; sb += SOLVER_SC) if (int rc = launch(sb, std::min(sb + SOLVER_SC, max_total))) return rc;
     CK(cudaMemcpyAsync(s->hdiffs, s->diffs, max_total * sizeof(double), cudaMemcpyDeviceToHost, s->st));
     CK(cudaStreamSynchronize(s->st));
     int stop = -1;
@@ -171,7 +171,7 @@ static int run_sor(hg_state* s, double* x, long long nx_, double tol, int limit,
       const double dstop = s->hdiffs[stop];
       CK(cudaMemsetAsync(x, 0, nx_ * sizeof(double), s->st));
       CK(cudaMemsetAsync(s->diffs, 0, max_total * sizeof(double), s->st));
-      if (int rc = launch(0, stop + 1)) return rc;
+      for (int sb = 0; sb < stop + 1; sb += SOLVER_SC) if (int rc = launch(sb, std::min(sb + SOLVER_SC, stop + 1))) return rc;
       *out_iter = stop; *out_diff = dstop;
       return 0;
     }
@@ -180,6 +180,7 @@ static int run_sor(hg_state* s, double* x, long long nx_, double tol, int limit,
     return 0;
   }
   int chunk = s->cfg.pressure_sweeps_per_check > 0 ? s->cfg.pressure_sweeps_per_check : 128;
+  if (chunk > SOLVER_SC) chunk = SOLVER_SC;
   int done = 0;
   while (done < max_total) {
     int n = std::min(chunk, max_total - done);
@@ -747,8 +748,8 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lu, k_lu_persistent<2>, SOLVER_THREADS, 0);
   }
   if (occ_gs < 1 || occ_lu < 1) return fail_create(s, HG_ERR_CUDA, "solver kernel does not fit on an SM");
-  s->grid_solver = prop.multiProcessorCount * std::min(occ_gs, 8);
-  s->grid_lu = prop.multiProcessorCount * std::min(occ_lu, 2);
+  s->grid_solver = prop.multiProcessorCount * std::min(occ_gs, 1);
+  s->grid_lu = prop.multiProcessorCount * std::min(occ_lu, 1);
 
   // hyperplane tile table for the ordered sweeps (hg_solvers.cuh)
   {
