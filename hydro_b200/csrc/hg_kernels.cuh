@@ -379,10 +379,19 @@ DV double face_coeff(const Geo& g, const double* __restrict__ dc, int d, const F
 // the sheared layout; the sweep kernels regenerate the off-diagonals A/(h d_f) from it.
 template <int DIM>
 __global__ void k_prhs(Geo g, const double* __restrict__ Fs, const double* __restrict__ dc,
-                       double* __restrict__ RP, double* __restrict__ D) {
+                       double* __restrict__ RP, double* __restrict__ CX, double* __restrict__ CY, double* __restrict__ CZ) {
   CELL_LOOP_PROLOG(g)
   const long long cs = shidx(g, i, j, k);
-  D[cs] = dc[c];
+  // face coefficients of the cell's plus faces for the sweep kernel (0 when the face is not inner)
+  {
+    double cf[3] = {0., 0., 0.};
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      FaceInfo f = face_info<DIM>(g, d, i + (d == 0), j + (d == 1), k + (d == 2));
+      if (f.type == FT_INNER) cf[d] = face_coeff<DIM>(g, dc, d, f);
+    }
+    CX[cs] = cf[0]; CY[cs] = cf[1]; if (DIM > 2) CZ[cs] = cf[2];
+  }
   if (cell_excl(g, i, j, k)) { RP[cs] = 0.; return; }
   if (c == g.pfix) { RP[cs] = -g.pfix_value; return; }
   double cst = 0.;

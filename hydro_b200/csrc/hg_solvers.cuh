@@ -60,7 +60,9 @@ DV void fill_step_table(const TileTable& tt, const StepTiles& st, int* sc) {
 
 // ---------------------------------------------------------------- pressure: Gauss-Seidel / SOR
 struct GsArgs {
-  const double* D;     // diagonal field d_c (fc_diag_coeff_), sheared
+  const double* CX;    // c_f = A/(h d_f) of the x+ face of each cell (0 when that face is not inner), sheared
+  const double* CY;    // same for the y+ face
+  const double* CZ;    // same for the z+ face
   const double* RP;    // row constants, sheared
   double* PP;          // solution, sheared; must be zero on entry for sweep 0 (linear.hpp:686)
   double* diff;        // per-sweep max |value - x| (linear.hpp:707), indexed by absolute sweep number
@@ -69,14 +71,9 @@ struct GsArgs {
   TileTable tt;
 };
 
-// off-diagonal coupling c_f = A/(h d_f) through a face of direction d between this cell (d0) and a
-// neighbour with diagonal value dn (fluid.hpp:957-964): d_f = d[cm]*0.5 + d[cp]*0.5, coeff = -A/(h d_f)
-DV double gs_cf(const Geo& g, int d, double dn, double d0) {
-  const double dfc = dn * (1. - 0.5) + d0 * 0.5;
-  const double coeff = -g.area[d] / (g.h[d] * dfc);
-  return -coeff;
-}
-
+// Rows of the pressure-correction system (fluid.hpp:972-1014) are rebuilt on the fly from the three face
+// coefficient fields: diagonal = ordered sum of the six face coefficients (absent faces store 0, and
+// x + 0 == x, so the reference's "merge only existing terms" gives the same bits), off-diagonals = -c_f.
 template <int DIM, bool EXCL>
 __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_gs_persistent(Geo g, GsArgs a) {
   cg::grid_group grid = cg::this_grid();
@@ -101,38 +98,24 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_gs_persistent(Geo g, GsAr
         const long long cs = ((long long)kp * g.n[1] + j) * nx + i;
         const long long c = i + g.sy * j + g.sz * k;
         // neighbours in the sheared layout: x-: cs-PS-1, y-: cs-PS-nx, z-: cs-PS, x+: cs+PS+1, y+: cs+PS+nx, z+: cs+PS
-        bool in_xm = i > 0, in_xp = i + 1 < nx, in_ym = j > 0, in_yp = j + 1 < g.n[1];
-        bool in_zm = DIM > 2 && k > 0, in_zp = DIM > 2 && k + 1 < g.n[2];
+        const bool in_xm = i > 0, in_xp = i + 1 < nx, in_ym = j > 0, in_yp = j + 1 < g.n[1];
+        const bool in_zm = DIM > 2 && k > 0, in_zp = DIM > 2 && k + 1 < g.n[2];
         bool ident = c == g.pfix;
-        if (EXCL) {
-          ident = ident || g.excl[c] != 0;
-          in_xm = in_xm && g.excl[c - 1] == 0; in_xp = in_xp && g.excl[c + 1] == 0;
-          in_ym = in_ym && g.excl[c - g.sy] == 0; in_yp = in_yp && g.excl[c + g.sy] == 0;
-          if (DIM > 2) { in_zm = in_zm && g.excl[c - g.sz] == 0; in_zp = in_zp && g.excl[c + g.sz] == 0; }
-        }
+        if (EXCL) ident = ident || g.excl[c] != 0;
+        // all loads up front (independent addresses)
         const double rhs = a.RP[cs];
         const double xold = __ldcg(&a.PP[cs]);
-        const double d0 = a.D[cs];
-        // issue all neighbour loads up front (independent addresses)
-        const double dxm = in_xm ? a.D[cs - PS - 1] : 1., dxp = in_xp ? a.D[cs + PS + 1] : 1.;
-        const double dym = in_ym ? a.D[cs - PS - nx] : 1., dyp = in_yp ? a.D[cs + PS + nx] : 1.;
-        const double dzm = in_zm ? a.D[cs - PS] : 1., dzp = in_zp ? a.D[cs + PS] : 1.;
+        const double cxp = a.CX[cs], cyp = a.CY[cs], czp = DIM > 2 ? a.CZ[cs] : 0.;
+        const double cxm = in_xm ? a.CX[cs - PS - 1] : 0., cym = in_ym ? a.CY[cs - PS - nx] : 0.;
+        const double czm = in_zm ? a.CZ[cs - PS] : 0.;
         const double pxm = in_xm ? __ldcg(&a.PP[cs - PS - 1]) : 0., pxp = in_xp ? __ldcg(&a.PP[cs + PS + 1]) : 0.;
         const double pym = in_ym ? __ldcg(&a.PP[cs - PS - nx]) : 0., pyp = in_yp ? __ldcg(&a.PP[cs + PS + nx]) : 0.;
         const double pzm = in_zm ? __ldcg(&a.PP[cs - PS]) : 0., pzp = in_zp ? __ldcg(&a.PP[cs + PS]) : 0.;
         double diag = 1., sum = 0.;
         if (!ident) {
-          const double cxm = gs_cf(g, 0, dxm, d0), cxp = gs_cf(g, 0, dxp, d0);
-          const double cym = gs_cf(g, 1, dym, d0), cyp = gs_cf(g, 1, dyp, d0);
-          const double czm = DIM > 2 ? gs_cf(g, 2, dzm, d0) : 0., czp = DIM > 2 ? gs_cf(g, 2, dzp, d0) : 0.;
-          // diagonal: contributions merged in face order x-,x+,y-,y+,z-,z+ (fluid.hpp:979-984)
-          bool have = false; diag = 0.;
-          if (in_xm) { diag = have ? diag + cxm : cxm; have = true; }
-          if (in_xp) { diag = have ? diag + cxp : cxp; have = true; }
-          if (in_ym) { diag = have ? diag + cym : cym; have = true; }
-          if (in_yp) { diag = have ? diag + cyp : cyp; have = true; }
-          if (in_zm) { diag = have ? diag + czm : czm; have = true; }
-          if (in_zp) { diag = have ? diag + czp : czp; have = true; }
+          // diagonal: face order x-,x+,y-,y+,z-,z+ (fluid.hpp:979-984)
+          diag = cxm + cxp; diag = diag + cym; diag = diag + cyp;
+          if (DIM > 2) { diag = diag + czm; diag = diag + czp; }
           // off-diagonal terms in ascending index order z-,y-,x-,x+,y+,z+ (linear.hpp:694-701);
           // terms toward the fixed-pressure cell were removed by SetKnownValue (fluid.hpp:1010)
           const long long pf = g.pfix;

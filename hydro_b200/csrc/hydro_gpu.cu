@@ -35,7 +35,7 @@ struct hg_state {
   double *force[3] = {}, *stforce[3] = {};
   double *gp[3] = {}, *fcr[3] = {}, *G[9] = {}, *fs[3] = {}, *dc = nullptr, *Fs = nullptr, *pc = nullptr;
   double *w1 = nullptr, *w2 = nullptr, *zero = nullptr;
-  double *A[7] = {}, *R[3] = {}, *X[3] = {}, *D = nullptr, *RP = nullptr, *PP = nullptr, *PPsave = nullptr;
+  double *A[7] = {}, *R[3] = {}, *X[3] = {}, *D = nullptr, *CYs = nullptr, *CZs = nullptr, *RP = nullptr, *PP = nullptr, *PPsave = nullptr;
   double* resid = nullptr;    // per-iteration convergence indicators of the current step (device, 4096)
   double* scal = nullptr;     // device scalars: [0] resid, [1] auto dt, [2..] stat (36), then diffs
   int* flag = nullptr;        // NaN flag
@@ -254,7 +254,7 @@ static int solve_pressure(hg_state* s) {
   int it = 0; double df = 0.;
   if (c.linear_solver_pressure == HG_LS_GAUSS_SEIDEL) {
     auto launch = [&](int sb, int se) -> int {
-      GsArgs a; a.D = s->D; a.RP = s->RP; a.PP = s->PP; a.diff = s->diffs; a.s_begin = sb; a.s_end = se;
+      GsArgs a; a.CX = s->D; a.CY = s->CYs; a.CZ = s->CZs; a.RP = s->RP; a.PP = s->PP; a.diff = s->diffs; a.s_begin = sb; a.s_end = se;
       a.omega = c.lu_relaxed_relaxation_factor; a.tt = s->tt;
       if (s->dim == 3) return s->any_excl ? coop_launch(s, k_gs_persistent<3, true>, s->grid_solver, s->geo, a, 0)
                                           : coop_launch(s, k_gs_persistent<3, false>, s->grid_solver, s->geo, a, 0);
@@ -440,7 +440,7 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
     DIMSEL(s, k_fstar, gb, 256, s->geo, a); }
   tpop(s);
   tpush(s, "fluid.5.pressure-system");
-  DIMSEL(s, k_prhs, gb, 256, s->geo, s->Fs, s->dc, s->RP, s->D);
+  DIMSEL(s, k_prhs, gb, 256, s->geo, s->Fs, s->dc, s->RP, s->D, s->CYs, s->CZs);
   tpop(s);
   tpush(s, "fluid.6.pressure-solve");
   if (int rc = solve_pressure(s)) return rc;
@@ -724,7 +724,7 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
   for (int q = 0; q < dim * dim && ok; ++q) ok = A_(&s->G[q], nc);
   for (int t = 0; t < 7 && ok; ++t) ok = A_(&s->A[t], s->nsh);
   for (int n = 0; n < dim && ok; ++n) ok = A_(&s->R[n], s->nsh) && A_(&s->X[n], s->nsh);
-  ok = ok && A_(&s->D, s->nsh) && A_(&s->RP, s->nsh) && A_(&s->PP, s->nsh) && A_(&s->PPsave, s->nsh);
+  ok = ok && A_(&s->D, s->nsh) && A_(&s->CYs, s->nsh) && A_(&s->CZs, dim > 2 ? s->nsh : 1) && A_(&s->RP, s->nsh) && A_(&s->PP, s->nsh) && A_(&s->PPsave, s->nsh);
   ok = ok && A_(&s->scal, 64) && A_(&s->resid, 4096);
   if (ok) { int* fp = nullptr; ok = dalloc(s, &fp, 4) == 0; s->flag = fp; }
   if (ok) { unsigned char* ep = nullptr; ok = dalloc(s, &ep, nc) == 0; s->excl = ep; }
