@@ -86,8 +86,16 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_gs_persistent(Geo g, GsAr
   for (int T = 0; T <= Tmax; ++T) {
     const StepTiles st = step_tiles(g, a.tt, T, S);
     fill_step_table(a.tt, st, sc);
+    // contiguous id range per slot (neighbouring tiles share rows -> cache reuse); first plane by binary search
+    const int chunk = (st.total + nslots - 1) / nslots;
+    const int id0 = gslot * chunk, id1 = min(id0 + chunk, st.total);
     int m = 0;
-    for (int id = gslot; id < st.total; id += nslots) {
+    if (id0 < id1) {
+      int lo = 0, hi = (st.kp_hi - st.kp_lo) >> 1;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (sc[mid] > id0) hi = mid; else lo = mid + 1; }
+      m = lo;
+    }
+    for (int id = id0; id < id1; ++id) {
       while (sc[m] <= id) ++m;
       const int kp = st.kp_lo + 2 * m;
       const int e = a.tt.tileoff[kp] + id - (m > 0 ? sc[m - 1] : 0);
@@ -211,8 +219,16 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_sor_matrix_persistent(Geo
   for (int T = 0; T <= Tmax; ++T) {
     const StepTiles st = step_tiles(g, a.tt, T, S);
     fill_step_table(a.tt, st, sc);
+    // contiguous id range per slot (neighbouring tiles share rows -> cache reuse); first plane by binary search
+    const int chunk = (st.total + nslots - 1) / nslots;
+    const int id0 = gslot * chunk, id1 = min(id0 + chunk, st.total);
     int m = 0;
-    for (int id = gslot; id < st.total; id += nslots) {
+    if (id0 < id1) {
+      int lo = 0, hi = (st.kp_hi - st.kp_lo) >> 1;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (sc[mid] > id0) hi = mid; else lo = mid + 1; }
+      m = lo;
+    }
+    for (int id = id0; id < id1; ++id) {
       while (sc[m] <= id) ++m;
       const int kp = st.kp_lo + 2 * m;
       const int e = a.tt.tileoff[kp] + id - (m > 0 ? sc[m - 1] : 0);
