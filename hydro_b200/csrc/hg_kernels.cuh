@@ -198,11 +198,12 @@ struct AsmArgs {
   double* R[3];            // sheared
   double* coeffsum;        // natural, nullable
   double coeffsum_div;     // dim
+  int out_sheared;         // 1: A/R are written in the sheared layout directly; 0: natural (k_shear3 follows)
 };
 template <int DIM, int KIND, int NCOMP>
 __global__ void k_assemble(Geo g, AsmArgs a) {
   CELL_LOOP_PROLOG(g)
-  const long long cs = shidx(g, i, j, k);
+  const long long cs = a.out_sheared ? shidx(g, i, j, k) : c;
   if (cell_excl(g, i, j, k)) {   // conv_diff.hpp:222-226
 #pragma unroll
     for (int t = 0; t < 7; ++t) if (DIM > 2 || (t != CZM && t != CZP)) a.A[t][cs] = (t == CD) ? 1. : 0.;
@@ -378,10 +379,10 @@ DV double face_coeff(const Geo& g, const double* __restrict__ dc, int d, const F
 // K_prhs: constants of the pressure-correction rows (fluid.hpp:972-1014) and the diagonal field in
 // the sheared layout; the sweep kernels regenerate the off-diagonals A/(h d_f) from it.
 template <int DIM>
-__global__ void k_prhs(Geo g, const double* __restrict__ Fs, const double* __restrict__ dc,
+__global__ void k_prhs(Geo g, const double* __restrict__ Fs, const double* __restrict__ dc, int out_sheared,
                        double* __restrict__ RP, double* __restrict__ CX, double* __restrict__ CY, double* __restrict__ CZ) {
   CELL_LOOP_PROLOG(g)
-  const long long cs = shidx(g, i, j, k);
+  const long long cs = out_sheared ? shidx(g, i, j, k) : c;
   // face coefficients of the cell's plus faces for the sweep kernel (0 when the face is not inner)
   {
     double cf[3] = {0., 0., 0.};
@@ -678,4 +679,28 @@ template <int DIM>
 __global__ void k_from_sheared(Geo g, const double* __restrict__ in, double* __restrict__ out) {
   CELL_LOOP_PROLOG(g)
   out[c] = in[shidx(g, i, j, k)];
+}
+
+// natural -> sheared layout for up to 10 arrays through a 32x32 (i,k) shared-memory tile at fixed j: a
+// diagonal i+k = const of the tile is a contiguous run of the sheared array, written by one warp.
+struct ShearArgs { const double* in[10]; double* out[10]; int narr; };
+__global__ void __launch_bounds__(256) k_shear3(Geo g, ShearArgs a) {
+  __shared__ double tile[32][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i0 = blockIdx.x * 32, j = blockIdx.y, k0 = blockIdx.z * 32;
+  for (int q = 0; q < a.narr; ++q) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int kl = ty + 8 * r;
+      if (i0 + tx < g.n[0] && k0 + kl < g.n[2]) tile[kl][tx] = a.in[q][cidx(g, i0 + tx, j, k0 + kl)];
+    }
+    __syncthreads();
+    for (int d = ty; d < 63; d += 8) {
+      const int il = (d > 31 ? d - 31 : 0) + tx;
+      const int kl = d - il;
+      if (il <= 31 && kl >= 0 && kl <= 31 && i0 + il < g.n[0] && k0 + kl < g.n[2])
+        a.out[q][shidx(g, i0 + il, j, k0 + kl)] = tile[kl][il];
+    }
+    __syncthreads();
+  }
 }

@@ -23,6 +23,32 @@ constexpr int SOLVER_SLOTS = 4;                       // tile slots per CTA
 constexpr int SOLVER_THREADS = SOLVER_TILE * SOLVER_SLOTS;   // 1024: one CTA per SM, 148 CTAs -> cheap grid barrier
 constexpr int SOLVER_SC = 1024;                       // max sweeps in flight per launch (shared table)
 
+// Grid-wide barrier for the persistent (cooperatively launched, hence co-resident) solver kernels:
+// one atomic arrival per CTA plus a generation word.  Cheaper than cg::grid_group::sync(), which also
+// invalidates L1 on every poll; data exchanged between SMs across the barrier (the solution vector)
+// is therefore always read with ld.global.cg (__ldcg).
+// The host zeroes the arrival counter before every launch; barrier number `epoch` (0,1,2,...) is complete
+// when the counter reaches (epoch+1)*nblocks.  Arrival is a release atomic, the poll an acquire load, so the
+// critical path is one atomic plus one load round trip through L2.
+DV void grid_barrier(unsigned long long* bar, unsigned int nblocks, unsigned int& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long target = (unsigned long long)(epoch + 1u) * nblocks;
+    unsigned long long old;
+    asm volatile("atom.add.release.gpu.global.u64 %0, [%1], 1;" : "=l"(old) : "l"(bar) : "memory");
+    if (old + 1ull < target) {
+      unsigned long long cur;
+      do {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(cur) : "l"(bar) : "memory");
+      } while (cur < target);
+    } else {
+      __threadfence();
+    }
+  }
+  ++epoch;
+  __syncthreads();
+}
+
 // Hyperplane tiles.  A tile is SOLVER_BY consecutive rows j x SOLVER_BX consecutive i of one plane
 // k' = i+j+k; only tiles that contain at least one cell are listed (built once per mesh on the host).
 struct TileTable {
@@ -30,6 +56,7 @@ struct TileTable {
   const int* tile_i0;    // first i of the tile
   const int* tileoff;    // [np+1] first tile of plane k'
   const int* cum2;       // [np] tiles of planes k', k'-2, k'-4, ... (same-parity running sum)
+  unsigned long long* bar;   // grid barrier arrival counter (zeroed by the host before each launch)
 };
 // cell handled by this thread in tile e of plane kp
 DV bool tile_cell(const Geo& g, const TileTable& tt, int e, int kp, int& i, int& j, int& k) {
@@ -76,13 +103,13 @@ struct GsArgs {
 // x + 0 == x, so the reference's "merge only existing terms" gives the same bits), off-diagonals = -c_f.
 template <int DIM, bool EXCL>
 __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_gs_persistent(Geo g, GsArgs a) {
-  cg::grid_group grid = cg::this_grid();
   __shared__ int sc[SOLVER_SC];
   const int S = a.s_end - a.s_begin;
   const int Tmax = (g.np - 1) + 2 * (S - 1);
   const long long PS = (long long)g.n[1] * g.n[0];   // plane stride of the sheared layout
   const int nx = g.n[0];
   const int gslot = blockIdx.x * SOLVER_SLOTS + (threadIdx.x / SOLVER_TILE), nslots = gridDim.x * SOLVER_SLOTS;
+  unsigned int epoch = 0;
   for (int T = 0; T <= Tmax; ++T) {
     const StepTiles st = step_tiles(g, a.tt, T, S);
     fill_step_table(a.tt, st, sc);
@@ -144,7 +171,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_gs_persistent(Geo g, GsAr
       ac = warp_max(ac);
       if ((threadIdx.x & 31) == 0 && ac > 0.) atomic_max_nonneg(&a.diff[a.s_begin + s], ac);
     }
-    grid.sync();
+    grid_barrier(a.tt.bar, gridDim.x, epoch);
   }
 }
 
@@ -158,10 +185,10 @@ struct LuArgs {
 };
 template <int DIM>
 __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_lu_persistent(Geo g, LuArgs a) {
-  cg::grid_group grid = cg::this_grid();
   const long long PS = (long long)g.n[1] * g.n[0];
   const int nx = g.n[0];
   const int gslot = blockIdx.x * SOLVER_SLOTS + (threadIdx.x / SOLVER_TILE), nslots = gridDim.x * SOLVER_SLOTS;
+  unsigned int epoch = 0;
   // forward step (linear.hpp:537-548)
   for (int kp = 0; kp < g.np; ++kp) {
     for (int e = a.tt.tileoff[kp] + gslot; e < a.tt.tileoff[kp + 1]; e += nslots) {
@@ -179,7 +206,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_lu_persistent(Geo g, LuAr
         a.X[n][cs] = (-a.R[n][cs] - sum) / diag;
       }
     }
-    grid.sync();
+    grid_barrier(a.tt.bar, gridDim.x, epoch);
   }
   // backward step (linear.hpp:551-563)
   for (int kp = g.np - 1; kp >= 0; --kp) {
@@ -198,7 +225,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_lu_persistent(Geo g, LuAr
         a.X[n][cs] = __ldcg(&a.X[n][cs]) - sum / diag;
       }
     }
-    grid.sync();
+    grid_barrier(a.tt.bar, gridDim.x, epoch);
   }
 }
 
@@ -209,13 +236,13 @@ struct SorArgs {
 };
 template <int DIM>
 __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_sor_matrix_persistent(Geo g, SorArgs a) {
-  cg::grid_group grid = cg::this_grid();
   __shared__ int sc[SOLVER_SC];
   const int S = a.s_end - a.s_begin;
   const int Tmax = (g.np - 1) + 2 * (S - 1);
   const long long PS = (long long)g.n[1] * g.n[0];
   const int nx = g.n[0];
   const int gslot = blockIdx.x * SOLVER_SLOTS + (threadIdx.x / SOLVER_TILE), nslots = gridDim.x * SOLVER_SLOTS;
+  unsigned int epoch = 0;
   for (int T = 0; T <= Tmax; ++T) {
     const StepTiles st = step_tiles(g, a.tt, T, S);
     fill_step_table(a.tt, st, sc);
@@ -254,7 +281,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_sor_matrix_persistent(Geo
       ac = warp_max(ac);
       if ((threadIdx.x & 31) == 0 && ac > 0.) atomic_max_nonneg(&a.diff[a.s_begin + s], ac);
     }
-    grid.sync();
+    grid_barrier(a.tt.bar, gridDim.x, epoch);
   }
 }
 

@@ -35,6 +35,7 @@ struct hg_state {
   double *force[3] = {}, *stforce[3] = {};
   double *gp[3] = {}, *fcr[3] = {}, *G[9] = {}, *fs[3] = {}, *dc = nullptr, *Fs = nullptr, *pc = nullptr;
   double *w1 = nullptr, *w2 = nullptr, *zero = nullptr;
+  double *An[10] = {};   // natural-layout staging of rows/constants before the shear transpose (3-D)
   double *A[7] = {}, *R[3] = {}, *X[3] = {}, *D = nullptr, *CYs = nullptr, *CZs = nullptr, *RP = nullptr, *PP = nullptr, *PPsave = nullptr;
   double* resid = nullptr;    // per-iteration convergence indicators of the current step (device, 4096)
   double* scal = nullptr;     // device scalars: [0] resid, [1] auto dt, [2..] stat (36), then diffs
@@ -134,6 +135,7 @@ template <class K, class A>
 static int coop_launch(hg_state* s, K kern, int grid, Geo g, A args, int prof_slot = -1) {
   void* params[] = {(void*)&g, (void*)&args};
   cudaEvent_t e0 = nullptr, e1 = nullptr;
+  CK(cudaMemsetAsync(s->tt.bar, 0, sizeof(unsigned long long), s->st));   // grid barrier arrival counter
   if (s->profile_on && prof_slot >= 0) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s->st); }
   CK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(SOLVER_THREADS), params, 0, s->st));
   if (e0) { cudaEventRecord(e1, s->st); s->prof_ev[prof_slot].push_back({e0, e1}); }
@@ -276,6 +278,16 @@ static int solve_pressure(hg_state* s) {
     return HG_ERR_INVALID;
   }
   s->sweeps_total += it + 1; s->last_diff = df;
+  return 0;
+}
+
+// natural -> sheared copies of n arrays (3-D: tiled transpose; the 2-D kernels write sheared directly)
+static int shear_arrays(hg_state* s, double* const* in, double* const* out, int n) {
+  ShearArgs a; a.narr = n;
+  for (int q = 0; q < n; ++q) { a.in[q] = in[q]; a.out[q] = out[q]; }
+  dim3 grid((s->n[0] + 31) / 32, s->n[1], (s->n[2] + 31) / 32);
+  k_shear3<<<grid, 256, 0, s->st>>>(s->geo, a);
+  ++s->launches;
   return 0;
 }
 
@@ -422,11 +434,21 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
     a.rho = s->rho; a.mu = s->mu; a.F = s->F[L_IP];
     bdf_coeffs(s->dt, c.time_second_order, a.co);
     a.relax = c.velocity_relaxation_factor;
-    for (int t = 0; t < 7; ++t) a.A[t] = s->A[t];
     a.coeffsum = s->dc; a.coeffsum_div = (double)s->dim;
-    if (s->dim == 3) { k_assemble<3, K_VEL, 3><<<gb, 256, 0, s->st>>>(s->geo, a); }
-    else { k_assemble<2, K_VEL, 2><<<gb, 256, 0, s->st>>>(s->geo, a); }
-    ++s->launches;
+    if (s->dim == 3) {
+      a.out_sheared = 0;
+      for (int t = 0; t < 7; ++t) a.A[t] = s->An[t];
+      for (int n = 0; n < 3; ++n) a.R[n] = s->An[7 + n];
+      k_assemble<3, K_VEL, 3><<<gb, 256, 0, s->st>>>(s->geo, a);
+      ++s->launches;
+      double* outs[10]; for (int t = 0; t < 7; ++t) outs[t] = s->A[t]; for (int n = 0; n < 3; ++n) outs[7 + n] = s->R[n];
+      shear_arrays(s, s->An, outs, 10);
+    } else {
+      a.out_sheared = 1;
+      for (int t = 0; t < 7; ++t) a.A[t] = s->A[t];
+      k_assemble<2, K_VEL, 2><<<gb, 256, 0, s->st>>>(s->geo, a);
+      ++s->launches;
+    }
     if (c.linear_solver_velocity != HG_LS_LU) { s->err = "linear_solver_velocity: only lu runs on the GPU path"; return HG_ERR_INVALID; }
     if (int rc = solve_lu(s, s->dim)) return rc;
     if (s->dim == 3) { k_apply_corr<3, 3><<<gb, 256, 0, s->st>>>(s->geo, cp3(s->u[L_IP]), cp3(s->X), p3(s->u[L_IC])); }
@@ -440,7 +462,13 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
     DIMSEL(s, k_fstar, gb, 256, s->geo, a); }
   tpop(s);
   tpush(s, "fluid.5.pressure-system");
-  DIMSEL(s, k_prhs, gb, 256, s->geo, s->Fs, s->dc, s->RP, s->D, s->CYs, s->CZs);
+  if (s->dim == 3) {
+    DIMSEL(s, k_prhs, gb, 256, s->geo, s->Fs, s->dc, 0, s->An[0], s->An[1], s->An[2], s->An[3]);
+    double* outs[4] = {s->RP, s->D, s->CYs, s->CZs};
+    shear_arrays(s, s->An, outs, 4);
+  } else {
+    DIMSEL(s, k_prhs, gb, 256, s->geo, s->Fs, s->dc, 1, s->RP, s->D, s->CYs, s->CZs);
+  }
   tpop(s);
   tpush(s, "fluid.6.pressure-solve");
   if (int rc = solve_pressure(s)) return rc;
@@ -560,7 +588,7 @@ extern "C" int hg_heat_step(hg_handle s) {   // heat.hpp:69-84 + conv_diff.hpp:1
   bdf_coeffs(c.dt /* HeatSolver keeps the time step of its constructor (hydro2d.hpp:684) */, c.time_second_order_heat, a.co);
   a.relax = c.heat_relaxation_factor;
   for (int t = 0; t < 7; ++t) a.A[t] = s->A[t];
-  a.coeffsum = nullptr; a.coeffsum_div = 1.;
+  a.coeffsum = nullptr; a.coeffsum_div = 1.; a.out_sheared = 1;
   if (s->dim == 3) { k_assemble<3, K_TEMP, 1><<<gb, 256, 0, s->st>>>(s->geo, a); }
   else { k_assemble<2, K_TEMP, 1><<<gb, 256, 0, s->st>>>(s->geo, a); }
   ++s->launches;
@@ -723,6 +751,7 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
   for (int d = 0; d < dim && ok; ++d) ok = A_(&s->force[d], nc) && A_(&s->stforce[d], nc) && A_(&s->gp[d], nc) && A_(&s->fcr[d], nc) && A_(&s->fs[d], nc);
   for (int q = 0; q < dim * dim && ok; ++q) ok = A_(&s->G[q], nc);
   for (int t = 0; t < 7 && ok; ++t) ok = A_(&s->A[t], s->nsh);
+  for (int t = 0; t < 10 && ok && dim == 3; ++t) ok = A_(&s->An[t], nc);
   for (int n = 0; n < dim && ok; ++n) ok = A_(&s->R[n], s->nsh) && A_(&s->X[n], s->nsh);
   ok = ok && A_(&s->D, s->nsh) && A_(&s->CYs, s->nsh) && A_(&s->CZs, dim > 2 ? s->nsh : 1) && A_(&s->RP, s->nsh) && A_(&s->PP, s->nsh) && A_(&s->PPsave, s->nsh);
   ok = ok && A_(&s->scal, 64) && A_(&s->resid, 4096);
@@ -777,6 +806,9 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     cudaMemcpy(d_off, toff.data(), toff.size() * sizeof(int), cudaMemcpyHostToDevice);
     cudaMemcpy(d_c2, cum2.data(), cum2.size() * sizeof(int), cudaMemcpyHostToDevice);
     s->tt.tile_j0 = d_tj; s->tt.tile_i0 = d_ti; s->tt.tileoff = d_off; s->tt.cum2 = d_c2;
+    unsigned long long* d_bar = nullptr;
+    if (dalloc(s, &d_bar, 4, true)) return fail_create(s, HG_ERR_CUDA, "allocation failed: " + s->err);
+    s->tt.bar = d_bar;
   }
   // rigid box -> excluded cells (hydro2d.hpp:409-416)
   {
