@@ -11,6 +11,7 @@
 #include <cstring>
 #include <sstream>
 #include <string>
+#include <vector>
 
 #include "control/experiment.hpp"
 #include "hydro_gpu.hpp"
@@ -124,7 +125,12 @@ class hydro_gpu : public TModule {
     ex->timer_.Pop();
     dt = st_.dt; P_double["dt"] = dt;
     P_int["s"] = st_.simple_iterations; P_int["s_sum"] += st_.simple_iterations;
-    logger() << ".....s=" << st_.simple_iterations << ", Rs=" << st_.convergence_indicator;
+    {   // the per-iteration lines hydro<Mesh>::step() logs (hydro2d.hpp:1585-1586)
+      std::vector<double> rs(st_.simple_iterations > 0 ? st_.simple_iterations : 1);
+      int n = 0;
+      h_.Check(hg_last_residuals(h_.get(), rs.data(), static_cast<int>(rs.size()), &n));
+      for (int k = 0; k < n; ++k) logger() << ".....s=" << (k + 1) << ", Rs=" << rs[k];
+    }
     publish_stat();
   }
   void write_results(bool force = false) override {
