@@ -37,7 +37,7 @@ def cavity_sample():
     arrays = {}
     for m in re.finditer(r'<DataArray Name="(\w+)"[^>]*>\n(.*?)\n\s*</DataArray>', vts, re.S):
         arrays[m.group(1)] = np.array(m.group(2).split())
-    np.savez_compressed(os.path.join(GOLD, "cavity_sample.npz"), rs_tokens=rs_tokens,
+    np.savez_compressed(os.path.join(GOLD, "cavity_sample.npz"), rs_tokens=rs_tokens, vts_text=np.array(vts),
                         velocity_x=arrays["velocity_x"], velocity_y=arrays["velocity_y"],
                         pressure=arrays["pressure"], volume_fraction_0=arrays["volume_fraction_0"])
     print("cavity_sample: %d residuals, %d cells" % (len(rs_tokens), len(arrays["pressure"])))

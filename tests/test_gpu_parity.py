@@ -131,17 +131,20 @@ def test_gpu_bit_exact_from_identical_state(name):
     assert np.array_equal(gpu.residuals(), cpu.residuals())
 
 
-def test_gpu_cavity_sample_first_iterations():
-    """The reference's golden sample (examples/cavity/sample): the first 60 SIMPLE residuals printed
-    with 6 significant digits must equal the shipped exp.iter_history.plt tokens."""
+def test_gpu_reproduces_reference_cavity_sample():
+    """The reference's golden sample (examples/cavity/sample: 64^2, Re 3200, 1000 SIMPLE iterations x 101
+    Gauss-Seidel sweeps) on the GPU: all 1000 residuals equal the shipped exp.iter_history.plt tokens and the
+    ParaView file written from the device fields equals the shipped exp.field.0.vts byte for byte."""
+    from hydro_b200 import output
     from hydro_b200.capi import Hydro
     g = np.load(os.path.join(GOLD, "cavity_sample.npz"))
     p = cases.cavity_kat()
-    p["num_iterations_limit"] = 60
     gpu = Hydro(p)
-    gpu.step()
+    st = gpu.step()
+    assert st.simple_iterations == 1000
     tok = np.array(["%g" % v for v in gpu.residuals()])
-    assert np.array_equal(tok, g["rs_tokens"][:60])
+    assert np.array_equal(tok, g["rs_tokens"])
+    assert output.vts_text(gpu, p) == str(g["vts_text"])
 
 
 @pytest.mark.parametrize("n", [32, 48])

@@ -88,6 +88,10 @@ def test_oracle_reproduces_reference_cavity_sample():
                        ("VOLUME_FRACTION_0", "volume_fraction_0")):
         tok = np.array(["%g" % v for v in o.get(fname)])
         assert np.array_equal(tok, g[key]), key
+    # the ParaView writer of the GPU path (hydro_b200/output.py), fed from the oracle's fields, reproduces the
+    # shipped exp.field.0.vts byte for byte
+    from hydro_b200 import output
+    assert output.vts_text(o, cases.cavity_kat()) == str(g["vts_text"])
 
 
 def test_cavity_centre_line_against_literature():
