@@ -214,6 +214,8 @@ def run_b200(args, rank, local_rank, world):
            "d2h_bytes_per_step": len(outs) * cells * 8 + 8 * 40, "ms_per_step": e2e_sec * 1e3, "steps": Ke,
            "timing": "host wall clock around pinned H2D + hg_step + D2H, stream-synchronised, max over ranks"}
     if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
         return
     peak, peak_src = measured_peak()
     # roofline of the dominant kernel: the pipelined Gauss-Seidel sweep kernel (k_gs_persistent), one launch
@@ -255,6 +257,8 @@ def run_b200(args, rank, local_rank, world):
                        "l2": "working set %.1f GB per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)" % (cells * 8 * 90 / 1e9)},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
     print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def main():

@@ -423,6 +423,34 @@ __global__ void k_prhs(Geo g, const double* __restrict__ Fs, const double* __res
   RP[cs] = (g.pfix >= 0 && has_extra) ? rhs + extra : rhs;
 }
 
+// K_prows: explicit rows of the pressure-correction system (fluid.hpp:972-1014) for solvers that need the
+// matrix (lu_relaxed): diagonal = ordered sum of the face coefficients, off-diagonals -c_f, excluded and
+// fixed-pressure cells as identity rows, terms toward the fixed-pressure cell removed (SetKnownValue)
+template <int DIM>
+__global__ void k_prows(Geo g, const double* __restrict__ dc, int out_sheared, P7 A) {
+  CELL_LOOP_PROLOG(g)
+  const long long cs = out_sheared ? shidx(g, i, j, k) : c;
+  double coef[7] = {0, 0, 0, 0, 0, 0, 0};
+  if (cell_excl(g, i, j, k) || c == g.pfix) coef[CD] = 1.;
+  else {
+    const int tmap[6] = {CXM, CXP, CYM, CYP, CZM, CZP};
+    double diag = 0.; bool have = false;
+#pragma unroll
+    for (int q = 0; q < 2 * DIM; ++q) {
+      const int d = q >> 1, o = q & 1;
+      FaceInfo f = face_info<DIM>(g, d, i + (d == 0 ? o : 0), j + (d == 1 ? o : 0), k + (d == 2 ? o : 0));
+      if (f.type != FT_INNER) continue;
+      const double cf = face_coeff<DIM>(g, dc, d, f);
+      diag = have ? diag + cf : cf; have = true;
+      const long long nb = o ? f.cp : f.cm;
+      coef[tmap[q]] = (nb == g.pfix) ? 0. : -cf;
+    }
+    coef[CD] = diag;
+  }
+#pragma unroll
+  for (int t = 0; t < 7; ++t) if (DIM > 2 || (t != CZM && t != CZP)) A.p[t][cs] = coef[t];
+}
+
 // K_pcorr: p' back to the natural layout, p_curr = p_prev + alpha_p p' (fluid.hpp:1035-1038)
 template <int DIM>
 __global__ void k_pcorr(Geo g, const double* __restrict__ PP, const double* __restrict__ pprev, double alpha,

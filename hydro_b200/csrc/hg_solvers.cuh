@@ -229,6 +229,83 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_lu_persistent(Geo g, LuAr
   }
 }
 
+// ---------------------------------------------------------------- "lu_relaxed" (linear.hpp:592-650)
+// forward step: corr_i = (-f_i - sum_{j<i} a_ij corr_j) / (a_ii + relax), ordered -> hyperplane wavefront
+struct LurArgs { const double* A[7]; const double* F; double* corr; double relax; TileTable tt; };
+template <int DIM>
+__global__ void __launch_bounds__(SOLVER_THREADS, 1) k_lur_forward(Geo g, LurArgs a) {
+  const long long PS = (long long)g.n[1] * g.n[0];
+  const int nx = g.n[0];
+  const int gslot = blockIdx.x * SOLVER_SLOTS + (threadIdx.x / SOLVER_TILE), nslots = gridDim.x * SOLVER_SLOTS;
+  unsigned int epoch = 0;
+  for (int kp = 0; kp < g.np; ++kp) {
+    for (int e = a.tt.tileoff[kp] + gslot; e < a.tt.tileoff[kp + 1]; e += nslots) {
+      int i, j, k;
+      if (!tile_cell(g, a.tt, e, kp, i, j, k)) continue;
+      const long long cs = ((long long)kp * g.n[1] + j) * nx + i;
+      double sum = 0.;
+      if (DIM > 2 && k > 0) sum += a.A[CZM][cs] * __ldcg(&a.corr[cs - PS]);
+      if (j > 0) sum += a.A[CYM][cs] * __ldcg(&a.corr[cs - PS - nx]);
+      if (i > 0) sum += a.A[CXM][cs] * __ldcg(&a.corr[cs - PS - 1]);
+      a.corr[cs] = (-a.F[cs] - sum) / (a.A[CD][cs] + a.relax);
+    }
+    grid_barrier(a.tt.bar, gridDim.x, epoch);
+  }
+}
+// backward step: corr_i -= (sum_{j>i} a_ij res_j) / (a_ii + relax) -- the reference reads `res`, not `corr`
+// (linear.hpp:632), so this step has no recurrence
+template <int DIM>
+__global__ void k_lur_backward(Geo g, LurArgs a, const double* __restrict__ res) {
+  long long c_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long nc_ = (long long)g.n[0] * g.n[1] * g.n[2];
+  if (c_ >= nc_) return;
+  const int i = (int)(c_ % g.n[0]), j = (int)((c_ / g.n[0]) % g.n[1]), k = (int)(c_ / ((long long)g.n[0] * g.n[1]));
+  const long long cs = shidx(g, i, j, k);
+  const long long PS = (long long)g.n[1] * g.n[0];
+  double sum = 0.;
+  if (DIM > 2 && k + 1 < g.n[2]) sum += a.A[CZP][cs] * res[cs + PS];
+  if (j + 1 < g.n[1]) sum += a.A[CYP][cs] * res[cs + PS + g.n[0]];
+  if (i + 1 < g.n[0]) sum += a.A[CXP][cs] * res[cs + PS + 1];
+  a.corr[cs] -= sum / (a.A[CD][cs] + a.relax);
+}
+// res += corr, diff = max |corr| (linear.hpp:641-644)
+template <int DIM>
+__global__ void k_lur_update(Geo g, const double* __restrict__ corr, double* __restrict__ res, double* diff) {
+  long long c_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long nc_ = (long long)g.n[0] * g.n[1] * g.n[2];
+  double ac = 0.;
+  if (c_ < nc_) {
+    const int i = (int)(c_ % g.n[0]), j = (int)((c_ / g.n[0]) % g.n[1]), k = (int)(c_ / ((long long)g.n[0] * g.n[1]));
+    const long long cs = shidx(g, i, j, k);
+    const double cr = corr[cs];
+    res[cs] += cr;
+    ac = fabs(cr);
+    if (!(ac == ac)) ac = 0.;
+  }
+  ac = warp_max(ac);
+  if ((threadIdx.x & 31) == 0 && ac > 0.) atomic_max_nonneg(diff, ac);
+}
+// f = system.Evaluate(res): constant + sum over terms in ascending index order (linear.hpp:645-647)
+template <int DIM>
+__global__ void k_lur_residual(Geo g, LurArgs a, const double* __restrict__ R, const double* __restrict__ res, double* __restrict__ f) {
+  long long c_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long nc_ = (long long)g.n[0] * g.n[1] * g.n[2];
+  if (c_ >= nc_) return;
+  const int i = (int)(c_ % g.n[0]), j = (int)((c_ / g.n[0]) % g.n[1]), k = (int)(c_ / ((long long)g.n[0] * g.n[1]));
+  const long long cs = shidx(g, i, j, k);
+  const long long PS = (long long)g.n[1] * g.n[0];
+  const int nx = g.n[0];
+  double r = R[cs];
+  if (DIM > 2 && k > 0) r += res[cs - PS] * a.A[CZM][cs];
+  if (j > 0) r += res[cs - PS - nx] * a.A[CYM][cs];
+  if (i > 0) r += res[cs - PS - 1] * a.A[CXM][cs];
+  r += res[cs] * a.A[CD][cs];
+  if (i + 1 < nx) r += res[cs + PS + 1] * a.A[CXP][cs];
+  if (j + 1 < g.n[1]) r += res[cs + PS + nx] * a.A[CYP][cs];
+  if (DIM > 2 && k + 1 < g.n[2]) r += res[cs + PS] * a.A[CZP][cs];
+  f[cs] = r;
+}
+
 // ---------------------------------------------------------------- generic-matrix sweeps (hg_linear_solve and
 // pressure systems given explicitly): SOR with stored rows, same pipelining as k_gs_persistent
 struct SorArgs {

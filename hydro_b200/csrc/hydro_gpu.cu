@@ -251,6 +251,34 @@ static int run_jacobi(hg_state* s, double* const* rows, const double* D, const d
   return 0;
 }
 
+static int shear_arrays(hg_state* s, double* const* in, double* const* out, int n);
+// LuDecompositionRelaxed::Solve (linear.hpp:592-650) on sheared rows A, constants R; result in `res` (sheared).
+// Scratch: corr, f (sheared).  One host round trip per outer iteration (the stop test needs max|corr|).
+static int run_lu_relaxed(hg_state* s, const double* R, double* res, double* corr, double* f, double tol, int limit, double relax,
+                          int* out_iter, double* out_diff) {
+  if (int rc = ensure_sweep_capacity(s, 4)) return rc;
+  CK(cudaMemsetAsync(res, 0, s->nsh * sizeof(double), s->st));
+  CK(cudaMemsetAsync(corr, 0, s->nsh * sizeof(double), s->st));
+  CK(cudaMemcpyAsync(f, R, s->nsh * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
+  LurArgs a; for (int t = 0; t < 7; ++t) a.A[t] = s->A[t];
+  a.F = f; a.corr = corr; a.relax = relax; a.tt = s->tt;
+  const unsigned gb = nblk(s->nc);
+  size_t iter = 0; double diff = 0.;
+  do {
+    if (s->dim == 3) { if (int rc = coop_launch(s, k_lur_forward<3>, s->grid_lu, s->geo, a)) return rc; }
+    else { if (int rc = coop_launch(s, k_lur_forward<2>, s->grid_lu, s->geo, a)) return rc; }
+    DIMSEL(s, k_lur_backward, gb, 256, s->geo, a, res);
+    CK(cudaMemsetAsync(s->diffs, 0, sizeof(double), s->st));
+    DIMSEL(s, k_lur_update, gb, 256, s->geo, corr, res, s->diffs);
+    DIMSEL(s, k_lur_residual, gb, 256, s->geo, a, R, res, f);
+    CK(cudaMemcpyAsync(s->hdiffs, s->diffs, sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    CK(cudaStreamSynchronize(s->st));
+    diff = s->hdiffs[0];
+  } while (diff > tol && iter++ < (size_t)limit);
+  *out_iter = (int)iter; *out_diff = diff;
+  return 0;
+}
+
 static int solve_pressure(hg_state* s) {
   const hg_config& c = s->cfg;
   int it = 0; double df = 0.;
@@ -273,8 +301,21 @@ static int solve_pressure(hg_state* s) {
     // p_curr = p_prev + alpha p'
     DIMSEL(s, k_to_sheared, nblk(s->nc), 256, s->geo, s->pc, s->PP);
     DIMSEL(s, k_pcorr, nblk(s->nc), 256, s->geo, s->PP, s->p[L_IP], c.pressure_relaxation_factor, s->pc, s->p[L_IC]);
+  } else if (c.linear_solver_pressure == HG_LS_LU_RELAXED) {
+    P7 rows;
+    if (s->dim == 3) {
+      for (int t = 0; t < 7; ++t) rows.p[t] = s->An[t];
+      DIMSEL(s, k_prows, nblk(s->nc), 256, s->geo, s->dc, 0, rows);
+      shear_arrays(s, s->An, s->A, 7);
+    } else {
+      for (int t = 0; t < 7; ++t) rows.p[t] = s->A[t];
+      DIMSEL(s, k_prows, nblk(s->nc), 256, s->geo, s->dc, 1, rows);
+    }
+    if (int rc = run_lu_relaxed(s, s->RP, s->PP, s->X[0], s->X[1], c.lu_relaxed_tolerance, c.lu_relaxed_num_iters_limit,
+                                c.lu_relaxed_relaxation_factor, &it, &df)) return rc;
+    DIMSEL(s, k_pcorr, nblk(s->nc), 256, s->geo, s->PP, s->p[L_IP], c.pressure_relaxation_factor, s->pc, s->p[L_IC]);
   } else {
-    s->err = "linear_solver_pressure: only gauss_seidel and jacobi run on the GPU path";
+    s->err = "linear_solver_pressure: lu is not iterated for the pressure system on the GPU path";
     return HG_ERR_INVALID;
   }
   s->sweeps_total += it + 1; s->last_diff = df;
@@ -1009,6 +1050,9 @@ extern "C" int hg_linear_solve(hg_handle s, int solver, const double* const coef
     };
     const int save = s->cfg.pressure_sweeps_per_check;
     if (int rc = run_sor(s, s->PP, s->nsh, tol, limit, launch, &it, &df)) { s->cfg.pressure_sweeps_per_check = save; return rc; }
+    DIMSEL(s, k_from_sheared, gb, 256, s->geo, s->PP, s->pc);
+  } else if (solver == HG_LS_LU_RELAXED) {
+    if (int rc = run_lu_relaxed(s, s->R[0], s->PP, s->X[0], s->X[1], tol, limit, relax, &it, &df)) return rc;
     DIMSEL(s, k_from_sheared, gb, 256, s->geo, s->PP, s->pc);
   } else if (solver == HG_LS_JACOBI) {
     // natural-layout rows in G[0..6] (dim*dim >= 4; use A-sized scratch via from_sheared)

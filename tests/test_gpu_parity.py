@@ -95,8 +95,6 @@ def run_both(p, nsteps, tol=TOL, stat_tol=1e-11):
 @pytest.mark.parametrize("name", list(cases.GOLDEN_CASES))
 def test_gpu_matches_oracle_and_reference_fixture(name):
     p, nsteps = cases.GOLDEN_CASES[name]
-    if p["linear_solver_pressure"] == "lu_relaxed":
-        pytest.skip("lu_relaxed is not on the GPU path yet (SURVEY 8f rank 4)")
     # rt3d_8_jacobi_dtauto is an unstable flow (dt_auto lets dt jump): the 1-ulp difference between
     # device and host sin() in the initial velocity is amplified ~1e7 times in 3 steps; its exactness is
     # covered by test_gpu_bit_exact_from_identical_state instead
@@ -110,7 +108,7 @@ def test_gpu_matches_oracle_and_reference_fixture(name):
 
 
 @pytest.mark.parametrize("name", ["rt3d_16", "dam3d_32x10x10", "thermal2d_32x16", "cavity_16", "rt3d_8_jacobi_dtauto",
-                                  "dam2d_36x20", "rt3d_12x10x9"])
+                                  "dam2d_36x20", "rt3d_12x10x9", "cavity_12_lurelaxed"])
 def test_gpu_bit_exact_from_identical_state(name):
     """Started from bit-identical fields (the oracle's initial state uploaded through hg_set_field, which
     removes the 1-ulp difference between device and host sin() in the initial velocity), the CUDA path
@@ -211,13 +209,14 @@ def random_rows(o, seed):
 
 @pytest.mark.parametrize("case", ["rt3d_12x10x9", "cavity_16", "rt3d_16"])
 @pytest.mark.parametrize("solver,tol,limit", [("lu", 0.0, 0), ("gauss_seidel", 0.0, 40), ("gauss_seidel", 1e-6, 500),
-                                                ("jacobi", 1e-5, 300), ("jacobi", 0.0, 21)])
+                                                ("jacobi", 1e-5, 300), ("jacobi", 0.0, 21), ("lu_relaxed", 1e-9, 40),
+                                                ("lu_relaxed", 0.0, 5)])
 def test_linear_solve(case, solver, tol, limit):
     from hydro_b200.capi import Hydro
     p, _ = cases.GOLDEN_CASES[case]
     gpu, cpu = Hydro(p), Oracle(p)
     rows, rhs = random_rows(cpu, 7)
-    relax = 1.3 if solver == "gauss_seidel" else 0.8
+    relax = 1.3 if solver == "gauss_seidel" else (0.4 if solver == "lu_relaxed" else 0.8)
     xg, ig, dg = gpu.linear_solve(solver, rows, rhs, tol, limit, relax)
     xc, ic, dc = cpu.linear_solve(solver, rows, rhs, tol, limit, relax)
     assert ig == ic
