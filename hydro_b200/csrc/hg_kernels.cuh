@@ -404,7 +404,7 @@ __global__ void k_prhs(Geo g, const double* __restrict__ Fs, const double* __res
     cst += Fs[fidx(g, d, fi, fj, fk)] * (o ? 1. : -1.);
   }
   double rhs = cst + -(0. * g.vol);
-  if (g.pfix >= 0) {
+  if (g.pfix != HG_NO_CELL) {
     // SetKnownValue (linear.hpp:238-250): rows coupling to the fixed cell get value*coeff added, in
     // ascending order of the fixed cell's neighbours (fluid.hpp:1002-1011 loops over all cells once)
 #pragma unroll
@@ -420,7 +420,7 @@ __global__ void k_prhs(Geo g, const double* __restrict__ Fs, const double* __res
     }
   }
   (void)has_extra;
-  RP[cs] = (g.pfix >= 0 && has_extra) ? rhs + extra : rhs;
+  RP[cs] = (g.pfix != HG_NO_CELL && has_extra) ? rhs + extra : rhs;
 }
 
 // K_prows: explicit rows of the pressure-correction system (fluid.hpp:972-1014) for solvers that need the
@@ -686,7 +686,12 @@ __global__ void k_init_flux(Geo g, CP3 u, double mv0, double mv1, double mv2, do
 }
 __global__ void k_excl_mask(Geo g, double bx0, double bx1, double bx2, double by0, double by1, double by2,
                             unsigned char* excl, int* any) {
-  CELL_LOOP_PROLOG(g)
+  // covers the halo planes too (global coordinates make them consistent without an exchange)
+  long long c_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nxy = (long long)g.n[0] * g.n[1];
+  if (c_ >= nxy * (g.n[2] + g.zlo + g.zhi)) return;
+  const int i = (int)(c_ % g.n[0]), j = (int)((c_ / g.n[0]) % g.n[1]), k = (int)(c_ / nxy) - g.zlo;
+  const long long c = cidx(g, i, j, k);
   double x[3]; cell_center(g, i, j, k, x);
   const double lb[3] = {bx0, bx1, bx2}, rt[3] = {by0, by1, by2};
   const bool in = rect_inside(lb, rt, x, g.dim);

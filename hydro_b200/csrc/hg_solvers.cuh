@@ -130,11 +130,11 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_gs_persistent(Geo g, GsAr
       int i, j, k;
       double ac = 0.;
       if (tile_cell(g, a.tt, e, kp, i, j, k)) {
-        const long long cs = ((long long)kp * g.n[1] + j) * nx + i;
+        const long long cs = ((long long)(kp + 1) * g.n[1] + j) * nx + i;
         const long long c = i + g.sy * j + g.sz * k;
         // neighbours in the sheared layout: x-: cs-PS-1, y-: cs-PS-nx, z-: cs-PS, x+: cs+PS+1, y+: cs+PS+nx, z+: cs+PS
         const bool in_xm = i > 0, in_xp = i + 1 < nx, in_ym = j > 0, in_yp = j + 1 < g.n[1];
-        const bool in_zm = DIM > 2 && k > 0, in_zp = DIM > 2 && k + 1 < g.n[2];
+        const bool in_zm = DIM > 2 && (k > 0 || g.zlo > 0), in_zp = DIM > 2 && (k + 1 < g.n[2] || g.zhi > 0);
         bool ident = c == g.pfix;
         if (EXCL) ident = ident || g.excl[c] != 0;
         // all loads up front (independent addresses)
@@ -194,8 +194,8 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_lu_persistent(Geo g, LuAr
     for (int e = a.tt.tileoff[kp] + gslot; e < a.tt.tileoff[kp + 1]; e += nslots) {
       int i, j, k;
       if (!tile_cell(g, a.tt, e, kp, i, j, k)) continue;
-      const long long cs = ((long long)kp * g.n[1] + j) * nx + i;
-      const bool zm = DIM > 2 && k > 0, ym = j > 0, xm = i > 0;
+      const long long cs = ((long long)(kp + 1) * g.n[1] + j) * nx + i;
+      const bool zm = DIM > 2 && (k > 0 || g.zlo > 0), ym = j > 0, xm = i > 0;
       const double azm = zm ? a.A[CZM][cs] : 0., aym = ym ? a.A[CYM][cs] : 0., axm = xm ? a.A[CXM][cs] : 0.;
       const double diag = a.A[CD][cs];
       for (int n = 0; n < a.ncomp; ++n) {
@@ -213,8 +213,8 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_lu_persistent(Geo g, LuAr
     for (int e = a.tt.tileoff[kp] + gslot; e < a.tt.tileoff[kp + 1]; e += nslots) {
       int i, j, k;
       if (!tile_cell(g, a.tt, e, kp, i, j, k)) continue;
-      const long long cs = ((long long)kp * g.n[1] + j) * nx + i;
-      const bool zp = DIM > 2 && k + 1 < g.n[2], yp = j + 1 < g.n[1], xp = i + 1 < nx;
+      const long long cs = ((long long)(kp + 1) * g.n[1] + j) * nx + i;
+      const bool zp = DIM > 2 && (k + 1 < g.n[2] || g.zhi > 0), yp = j + 1 < g.n[1], xp = i + 1 < nx;
       const double azp = zp ? a.A[CZP][cs] : 0., ayp = yp ? a.A[CYP][cs] : 0., axp = xp ? a.A[CXP][cs] : 0.;
       const double diag = a.A[CD][cs];
       for (int n = 0; n < a.ncomp; ++n) {
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_lur_forward(Geo g, LurArg
     for (int e = a.tt.tileoff[kp] + gslot; e < a.tt.tileoff[kp + 1]; e += nslots) {
       int i, j, k;
       if (!tile_cell(g, a.tt, e, kp, i, j, k)) continue;
-      const long long cs = ((long long)kp * g.n[1] + j) * nx + i;
+      const long long cs = ((long long)(kp + 1) * g.n[1] + j) * nx + i;
       double sum = 0.;
       if (DIM > 2 && k > 0) sum += a.A[CZM][cs] * __ldcg(&a.corr[cs - PS]);
       if (j > 0) sum += a.A[CYM][cs] * __ldcg(&a.corr[cs - PS - nx]);
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_sor_matrix_persistent(Geo
       int i, j, k;
       double ac = 0.;
       if (tile_cell(g, a.tt, e, kp, i, j, k)) {
-        const long long cs = ((long long)kp * g.n[1] + j) * nx + i;
+        const long long cs = ((long long)(kp + 1) * g.n[1] + j) * nx + i;
         double sum = 0.;
         if (DIM > 2 && k > 0) sum += a.A[CZM][cs] * __ldcg(&a.X[cs - PS]);
         if (j > 0) sum += a.A[CYM][cs] * __ldcg(&a.X[cs - PS - nx]);

@@ -37,6 +37,7 @@ struct hg_state {
   double *w1 = nullptr, *w2 = nullptr, *zero = nullptr;
   double *An[10] = {};   // natural-layout staging of rows/constants before the shear transpose (3-D)
   double *A[7] = {}, *R[3] = {}, *X[3] = {}, *D = nullptr, *CYs = nullptr, *CZs = nullptr, *RP = nullptr, *PP = nullptr, *PPsave = nullptr;
+  double* mailbox = nullptr; unsigned long long* xflags = nullptr;   // peer-written scratch (multi-GPU)
   double* resid = nullptr;    // per-iteration convergence indicators of the current step (device, 4096)
   double* scal = nullptr;     // device scalars: [0] resid, [1] auto dt, [2..] stat (36), then diffs
   int* flag = nullptr;        // NaN flag
@@ -57,6 +58,12 @@ struct hg_state {
   std::map<std::string, Timer> timers;
   std::vector<std::string> timer_stack;
   std::vector<void*> allocs;
+  // one device arena holds every fp64 array: a peer GPU maps it once (CUDA IPC) and reaches any array of
+  // this rank at a known offset (the layout is a pure function of the configuration and the rank)
+  char* arena = nullptr; size_t arena_bytes = 0;
+  std::vector<size_t> arena_offs;              // offset of every allocation, in allocation order
+  int world = 1, rank = 0, k0 = 0, k1 = 0, nzg = 1;
+  long long nxy = 0, ncg = 0;
   bool profile_on = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[2];   // [0] pressure sweeps kernel, [1] lu kernel
   cudaEvent_t user_ev[8] = {};
@@ -737,7 +744,12 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
   if (cfg->sharp != 0.) return fail_create(nullptr, HG_ERR_INVALID, "sharp != 0 is not on the GPU path");
   for (int sd = 0; sd < 2 * cfg->dim; ++sd)
     if (cfg->condition_kind[sd] == HG_BC_OUTLET) return fail_create(nullptr, HG_ERR_INVALID, "outlet conditions are not on the GPU path");
-  if (cfg->world_size > 1) return fail_create(nullptr, HG_ERR_INVALID, "world_size > 1: use the slab driver (hydro_b200.parallel)");
+  if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size || cfg->world_size > 64)
+    return fail_create(nullptr, HG_ERR_INVALID, "bad world_size / rank");
+  if (cfg->world_size > 1 && (cfg->dim != 3 || cfg->Nz < 2 * cfg->world_size))
+    return fail_create(nullptr, HG_ERR_INVALID, "z-slab decomposition needs dim 3 and at least 2 planes per rank");
+  if (cfg->world_size > 1 && (cfg->linear_solver_pressure == HG_LS_LU_RELAXED || cfg->linear_solver_pressure == HG_LS_JACOBI))
+    return fail_create(nullptr, HG_ERR_INVALID, "multi-GPU slabs support gauss_seidel for the pressure system");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
     return fail_create(nullptr, HG_ERR_NO_DEVICE, "no CUDA device: the GPU path has no CPU fallback");
@@ -750,15 +762,25 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
   if (!coop) return fail_create(s, HG_ERR_CUDA, "device lacks cooperative launch");
   if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess) return fail_create(s, HG_ERR_CUDA, "stream create failed");
   const int dim = s->dim = cfg->dim;
-  s->n[0] = cfg->Nx; s->n[1] = cfg->Ny; s->n[2] = dim > 2 ? cfg->Nz : 1;
-  s->nc = (long long)s->n[0] * s->n[1] * s->n[2];
+  // z-slab owned by this rank (hydro_b200/parallel.py: slab_range)
+  s->world = cfg->world_size; s->rank = cfg->rank;
+  s->nzg = dim > 2 ? cfg->Nz : 1;
+  { const int base = s->nzg / s->world, rem = s->nzg % s->world;
+    s->k0 = s->rank * base + std::min(s->rank, rem); s->k1 = s->k0 + base + (s->rank < rem ? 1 : 0); }
+  s->n[0] = cfg->Nx; s->n[1] = cfg->Ny; s->n[2] = s->k1 - s->k0;
+  s->nxy = (long long)s->n[0] * s->n[1];
+  s->nc = s->nxy * s->n[2];
+  s->ncg = s->nxy * s->nzg;
   Geo& g = s->geo;
   memset(&g, 0, sizeof g);
   g.dim = dim; g.sy = s->n[0]; g.sz = (long long)s->n[0] * s->n[1];
+  g.k0 = s->k0; g.nzg = s->nzg;
+  g.zlo = s->rank > 0 ? HG_HALO : 0; g.zhi = s->rank + 1 < s->world ? HG_HALO : 0;
   g.vol = 1.;
+  const int nglob[3] = {cfg->Nx, cfg->Ny, s->nzg};
   for (int d = 0; d < 3; ++d) {
     g.n[d] = s->n[d]; g.lb[d] = cfg->A[d];
-    g.h[d] = d < dim ? (cfg->B[d] - cfg->A[d]) / s->n[d] : 1.;
+    g.h[d] = d < dim ? (cfg->B[d] - cfg->A[d]) / nglob[d] : 1.;
     if (d < dim) g.vol *= g.h[d];
   }
   for (int d = 0; d < 3; ++d) { g.area[d] = 1.; if (d < dim) for (int e = 0; e < dim; ++e) if (e != d) g.area[d] *= g.h[e]; }
@@ -768,37 +790,67 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     if (d < dim) s->nf += (long long)(s->n[0] + (d == 0)) * (s->n[1] + (d == 1)) * (s->n[2] + (d == 2));
   }
   g.np = s->n[0] + s->n[1] + s->n[2] - 2;
-  s->nsh = (long long)g.np * s->n[1] * s->n[0];
+  s->nsh = (long long)(g.np + 2) * s->n[1] * s->n[0];   // one extra plane at each end (slab halo cells)
   for (int sd = 0; sd < 6; ++sd) { g.bckind[sd] = cfg->condition_kind[sd]; for (int d = 0; d < 3; ++d) g.bcvel[sd][d] = cfg->condition_velocity[sd][d]; }
   g.bckind[6] = HG_BC_WALL;
   for (int d = 0; d < 3; ++d) { g.heat_lb[d] = cfg->heat_box_lb[d]; g.heat_rt[d] = cfg->heat_box_rt[d]; }
   g.heat_T = cfg->heat_box_temperature;
-  g.pfix = -1; g.pfix_value = cfg->pressure_fixed_value;
+  g.pfix = HG_NO_CELL; g.pfix_value = cfg->pressure_fixed_value;
   g.excl = nullptr;
 
-  hg_state* sck = s;
-  auto A_ = [&](double** p, long long n) -> bool { return dalloc(sck, p, n) == 0; };
-  bool ok = true;
+  // ---- arena layout: cell arrays carry HG_HALO planes on both sides (pointer = first owned cell)
   const long long nc = s->nc, nf = s->nf;
-  for (int l = 0; l < 4 && ok; ++l) {
-    for (int d = 0; d < dim && ok; ++d) ok = A_(&s->u[l][d], nc);
-    ok = ok && A_(&s->p[l], nc) && A_(&s->F[l], nf);
-    if (cfg->heat_enable && l < 3) ok = ok && A_(&s->T[l], nc);
-    for (int ph = 0; ph < cfg->num_phases && ok; ++ph) ok = A_(&s->pd[ph][l], nc);
+  auto layout = [&](hg_state* t, int nzl, char* base, std::vector<size_t>& offs) -> size_t {
+    size_t off = 0;
+    const long long nxy_ = s->nxy;
+    const long long ncell = nxy_ * (nzl + 2 * HG_HALO);
+    const int np_ = s->n[0] + s->n[1] + nzl - 2;
+    const long long nsh_ = (long long)(np_ + 2) * nxy_;
+    long long nf_ = 0;
+    for (int d = 0; d < dim; ++d) nf_ += (long long)(s->n[0] + (d == 0)) * (s->n[1] + (d == 1)) * (nzl + (d == 2));
+    auto take = [&](long long n) -> double* {
+      const size_t bytes = (((size_t)(n > 0 ? n : 1) * sizeof(double)) + 255) & ~(size_t)255;
+      const size_t o = off; off += bytes; offs.push_back(o);
+      return base ? (double*)(base + o) : nullptr;
+    };
+    auto cells = [&]() -> double* { double* q = take(ncell); return q ? q + HG_HALO * nxy_ : nullptr; };
+    hg_state& T = *t;
+    for (int l = 0; l < 4; ++l) {
+      for (int d = 0; d < dim; ++d) T.u[l][d] = cells();
+      T.p[l] = cells(); T.F[l] = take(nf_);
+      if (cfg->heat_enable && l < 3) T.T[l] = cells();
+      for (int ph = 0; ph < cfg->num_phases; ++ph) T.pd[ph][l] = cells();
+    }
+    for (int ph = 0; ph < cfg->num_phases; ++ph) { T.vf[ph] = cells(); T.pd_init[ph] = cells(); }
+    T.rho_raw = cells(); T.mu_raw = cells(); T.rho = cells(); T.mu = cells(); T.kc = cells();
+    T.dc = cells(); T.Fs = take(nf_); T.pc = cells(); T.w1 = cells(); T.w2 = cells(); T.zero = cells();
+    for (int d = 0; d < dim; ++d) { T.force[d] = cells(); T.stforce[d] = cells(); T.gp[d] = cells(); T.fcr[d] = cells(); T.fs[d] = cells(); }
+    for (int q = 0; q < dim * dim; ++q) T.G[q] = cells();
+    for (int q = 0; q < 7; ++q) T.A[q] = take(nsh_);
+    if (dim == 3) for (int q = 0; q < 10; ++q) T.An[q] = cells();
+    for (int n = 0; n < dim; ++n) { T.R[n] = take(nsh_); T.X[n] = take(nsh_); }
+    T.D = take(nsh_); T.CYs = take(nsh_); T.CZs = take(dim > 2 ? nsh_ : 1); T.RP = take(nsh_); T.PP = take(nsh_); T.PPsave = take(nsh_);
+    T.scal = take(64); T.resid = take(4096);
+    T.mailbox = take(64 * 128);   // [rank][128] doubles written by peers (hg_slab.cuh)
+    T.xflags = (unsigned long long*)take(64 * 4);   // [rank][4] exchange / solver handshake counters written by peers
+    return off;
+  };
+  {
+    std::vector<size_t> offs;
+    hg_state scratch_layout;   // pointers ignored in the measuring pass
+    s->arena_bytes = layout(&scratch_layout, s->n[2], nullptr, offs);
+    void* q = nullptr;
+    if (cudaMalloc(&q, s->arena_bytes) != cudaSuccess) return fail_create(s, HG_ERR_CUDA, "arena allocation failed (" + std::to_string(s->arena_bytes >> 20) + " MiB)");
+    s->allocs.push_back(q);
+    s->arena = (char*)q;
+    cudaMemsetAsync(q, 0, s->arena_bytes, s->st);
+    s->arena_offs.clear();
+    layout(s, s->n[2], s->arena, s->arena_offs);
   }
-  for (int ph = 0; ph < cfg->num_phases && ok; ++ph) ok = A_(&s->vf[ph], nc) && A_(&s->pd_init[ph], nc);
-  ok = ok && A_(&s->rho_raw, nc) && A_(&s->mu_raw, nc) && A_(&s->rho, nc) && A_(&s->mu, nc) && A_(&s->kc, nc);
-  ok = ok && A_(&s->dc, nc) && A_(&s->Fs, nf) && A_(&s->pc, nc) && A_(&s->w1, nc) && A_(&s->w2, nc) && A_(&s->zero, nc);
-  for (int d = 0; d < dim && ok; ++d) ok = A_(&s->force[d], nc) && A_(&s->stforce[d], nc) && A_(&s->gp[d], nc) && A_(&s->fcr[d], nc) && A_(&s->fs[d], nc);
-  for (int q = 0; q < dim * dim && ok; ++q) ok = A_(&s->G[q], nc);
-  for (int t = 0; t < 7 && ok; ++t) ok = A_(&s->A[t], s->nsh);
-  for (int t = 0; t < 10 && ok && dim == 3; ++t) ok = A_(&s->An[t], nc);
-  for (int n = 0; n < dim && ok; ++n) ok = A_(&s->R[n], s->nsh) && A_(&s->X[n], s->nsh);
-  ok = ok && A_(&s->D, s->nsh) && A_(&s->CYs, s->nsh) && A_(&s->CZs, dim > 2 ? s->nsh : 1) && A_(&s->RP, s->nsh) && A_(&s->PP, s->nsh) && A_(&s->PPsave, s->nsh);
-  ok = ok && A_(&s->scal, 64) && A_(&s->resid, 4096);
+  bool ok = true;
   if (ok) { int* fp = nullptr; ok = dalloc(s, &fp, 4) == 0; s->flag = fp; }
-  if (ok) { unsigned char* ep = nullptr; ok = dalloc(s, &ep, nc) == 0; s->excl = ep; }
-  if (!ok || cudaMallocHost((void**)&s->hscal, 64 * sizeof(double)) != cudaSuccess) return fail_create(s, HG_ERR_CUDA, "allocation failed: " + s->err);
+  if (ok) { unsigned char* ep = nullptr; ok = dalloc(s, &ep, s->nxy * (s->n[2] + 2 * HG_HALO)) == 0; s->excl = ep ? ep + HG_HALO * s->nxy : nullptr; }
+  if (!ok || cudaMallocHost((void**)&s->hscal, 64 * 128 * sizeof(double)) != cudaSuccess) return fail_create(s, HG_ERR_CUDA, "allocation failed: " + s->err);
   // unused component slots alias a zero array so structs of 3 pointers are always valid
   for (int d = dim; d < 3; ++d) {
     for (int l = 0; l < 4; ++l) s->u[l][d] = nullptr;
@@ -855,23 +907,24 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
   {
     int* anyflag = s->flag + 1;
     cudaMemsetAsync(anyflag, 0, sizeof(int), s->st);
-    k_excl_mask<<<nblk(nc), 256, 0, s->st>>>(g, cfg->box_A[0], cfg->box_A[1], cfg->box_A[2], cfg->box_B[0], cfg->box_B[1], cfg->box_B[2], s->excl, anyflag);
+    k_excl_mask<<<nblk(s->nxy * (s->n[2] + g.zlo + g.zhi)), 256, 0, s->st>>>(g, cfg->box_A[0], cfg->box_A[1], cfg->box_A[2], cfg->box_B[0], cfg->box_B[1], cfg->box_B[2], s->excl, anyflag);
     ++s->launches;
     int h = 0; cudaMemcpyAsync(&h, anyflag, sizeof(int), cudaMemcpyDeviceToHost, s->st); cudaStreamSynchronize(s->st);
     s->any_excl = h != 0;
     g.excl = s->any_excl ? s->excl : nullptr;
   }
-  // fixed pressure cell: FindNearestCell (mesh.hpp:411-420), first minimum in raw order
+  // fixed pressure cell: FindNearestCell (mesh.hpp:411-420), first minimum in (global) raw order
   if (cfg->pressure_fixed_enable) {
     long long best = 0; double bd = 0.;
-    for (int k = 0; k < s->n[2]; ++k) for (int j = 0; j < s->n[1]; ++j) for (int i = 0; i < s->n[0]; ++i) {
+    for (int k = 0; k < s->nzg; ++k) for (int j = 0; j < s->n[1]; ++j) for (int i = 0; i < s->n[0]; ++i) {
       double x[3] = {g.lb[0] + (i + 0.5) * g.h[0], g.lb[1] + (j + 0.5) * g.h[1], dim > 2 ? g.lb[2] + (k + 0.5) * g.h[2] : 0.};
       double sq = 0.; for (int d = 0; d < dim; ++d) { double e = x[d] - cfg->pressure_fixed_point[d]; sq += e * e; }
       double dd = std::sqrt(sq);
       long long c = i + g.sy * j + g.sz * k;
       if (c == 0) { bd = dd; best = 0; } else if (dd < bd) { bd = dd; best = c; }
     }
-    g.pfix = best;
+    const int kg = (int)(best / g.sz);
+    if (kg >= s->k0 - g.zlo && kg < s->k1 + g.zhi) g.pfix = best - (long long)s->k0 * g.sz;   // local index, may be in a halo plane
   }
   s->dt = cfg->dt; s->dt_adv = cfg->dt * cfg->advection_dt_factor;
 
