@@ -15,7 +15,7 @@ import numpy as np
 from .config import F, FACE_FIELDS, LINEAR_SOLVERS, HgConfig, HgStepStats, Params
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhydro_gpu.so")
+LIB_PATH = os.environ.get("HYDRO_GPU_LIB", os.path.join(_HERE, "libhydro_gpu.so"))
 _lib = None
 
 SYMBOLS = [

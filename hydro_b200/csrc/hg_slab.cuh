@@ -1,0 +1,151 @@
+// hg_slab.cuh -- z-slab decomposition over the GPUs of one node: peer-memory halo exchange, mailbox
+// all-gather for the global reductions and the per-step neighbour handshake of the pipelined sweeps.
+//
+// The reference has no decomposition (its MPI is a stub, source/main.cpp:26-28).  One process per GPU;
+// torch.distributed (NCCL) is only the plumbing that carries the CUDA IPC handles.  On the data path every
+// rank maps four kinds of peer buffers once (hg_ipc_export / hg_ipc_import):
+//   xbuf   exchange staging: a rank PACKS its boundary planes locally, raises a flag in the neighbours'
+//          memory, the neighbours PULL the planes over NVLink into their halo planes;
+//   mail   mailbox + flag words: every rank pushes its partial scalars (max-norms, CalcStat sums, NaN flags)
+//          into every rank's mailbox; the reduction is then done locally in rank order (deterministic and
+//          identical on all ranks, so the control flow -- iteration and sweep counts -- stays in lockstep);
+//   PP, X  the sheared solution arrays of the ordered sweeps: the thread that updates an interface cell also
+//          stores the new value into the neighbour's halo plane (the z- dependency of the upper slab in the same
+//          sweep, the z+ dependency of the lower slab in the next one), and the per-hyperplane grid barrier is
+//          extended by a system-scope flag handshake with both neighbours (hg_solvers.cuh).
+// Staging and mailbox are double-buffered by sequence parity: a rank can never be two exchanges ahead of a
+// neighbour, because every exchange needs that neighbour's flag.
+#pragma once
+#include "hg_device.cuh"
+
+constexpr int SLAB_MAX_ARRAYS = 16;
+constexpr int SLAB_MAIL = 1056;      // doubles per rank per mailbox round (per-sweep norms of a 1024-sweep chunk fit)
+constexpr int SLAB_MAX_WORLD = 56;
+// flag words (unsigned long long) stored after the mailbox doubles
+enum { SF_X_LO = 0, SF_X_HI = 1, SF_S_LO = 2, SF_S_HI = 3, SF_MAIL0 = 8 };
+
+struct Slab {
+  int world = 1, rank = 0, has_lo = 0, has_hi = 0;
+  int nz_lo = 0, np_glob = 0;
+  double* xbuf = nullptr;
+  double* mail = nullptr;
+  const double* xbuf_lo = nullptr;
+  const double* xbuf_hi = nullptr;
+  double* mail_peer[SLAB_MAX_WORLD + 8] = {};
+  double *PP_lo = nullptr, *PP_hi = nullptr;
+  double *X_lo[3] = {}, *X_hi[3] = {};
+  unsigned long long xseq = 0, mseq = 0, hseq = 0;
+  bool linked = false;
+};
+
+HD unsigned long long* slab_flags(double* mail, int world) {
+  return reinterpret_cast<unsigned long long*>(mail + 2LL * world * SLAB_MAIL);
+}
+
+DV unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+DV void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+struct PackArgs { const double* src[SLAB_MAX_ARRAYS]; int n, planes; };
+struct UnpackArgs { double* dst[SLAB_MAX_ARRAYS]; int n, planes; };
+
+HD long long xbuf_index(long long nxy, int parity, int dir, int arr, int plane, long long c2) {
+  return (((long long)(parity * 2 + dir) * SLAB_MAX_ARRAYS + arr) * HG_HALO + plane) * nxy + c2;
+}
+
+// boundary planes -> local staging: dir 0 = for the lower neighbour (my bottom planes), dir 1 = for the upper
+__global__ void k_slab_pack(Geo g, PackArgs a, double* __restrict__ xbuf, int parity, int has_lo, int has_hi) {
+  const long long nxy = (long long)g.n[0] * g.n[1];
+  const long long per = (long long)a.planes * nxy;
+  const long long total = per * a.n;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int arr = (int)(t / per);
+    const long long r = t % per;
+    const int pl = (int)(r / nxy);
+    const long long c2 = r % nxy;
+    if (has_lo) xbuf[xbuf_index(nxy, parity, 0, arr, pl, c2)] = a.src[arr][(long long)pl * nxy + c2];
+    if (has_hi) xbuf[xbuf_index(nxy, parity, 1, arr, pl, c2)] = a.src[arr][(long long)(g.n[2] - a.planes + pl) * nxy + c2];
+  }
+}
+
+// raise "staging of exchange v is complete" in the neighbours' memory
+__global__ void k_slab_signal(unsigned long long* flag_in_lower, unsigned long long* flag_in_upper, unsigned long long v) {
+  __threadfence_system();
+  if (flag_in_lower) st_release_sys(flag_in_lower, v);
+  if (flag_in_upper) st_release_sys(flag_in_upper, v);
+}
+
+// wait for the neighbours' flags, then pull their staged planes into my halo planes
+__global__ void k_slab_unpack(Geo g, UnpackArgs a, const double* xbuf_lo, const double* xbuf_hi, int parity,
+                              const unsigned long long* myflags, unsigned long long v) {
+  if (threadIdx.x == 0) {
+    if (xbuf_lo) while (ld_acquire_sys(&myflags[SF_X_LO]) < v) {}
+    if (xbuf_hi) while (ld_acquire_sys(&myflags[SF_X_HI]) < v) {}
+  }
+  __syncthreads();
+  const long long nxy = (long long)g.n[0] * g.n[1];
+  const long long per = (long long)a.planes * nxy;
+  const long long total = per * a.n;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int arr = (int)(t / per);
+    const long long r = t % per;
+    const int pl = (int)(r / nxy);
+    const long long c2 = r % nxy;
+    // lower neighbour staged its TOP planes in dir 1 -> my planes -planes .. -1
+    if (xbuf_lo) a.dst[arr][(long long)(pl - a.planes) * nxy + c2] = __ldcv(&xbuf_lo[xbuf_index(nxy, parity, 1, arr, pl, c2)]);
+    // upper neighbour staged its BOTTOM planes in dir 0 -> my planes n[2] .. n[2]+planes-1
+    if (xbuf_hi) a.dst[arr][(long long)(g.n[2] + pl) * nxy + c2] = __ldcv(&xbuf_hi[xbuf_index(nxy, parity, 0, arr, pl, c2)]);
+  }
+}
+
+// mailbox all-gather: push n doubles into every rank's mailbox slot [parity][me], then raise flag[me] there
+struct MailPeers { double* mail[SLAB_MAX_WORLD + 8]; };
+__global__ void k_mail_post(MailPeers p, const double* __restrict__ vals, int n, int parity, int me, int world, unsigned long long v) {
+  const int t = threadIdx.x;
+  for (int q = t; q < n; q += blockDim.x) {
+    const double x = vals[q];
+    for (int r = 0; r < world; ++r) p.mail[r][((long long)parity * world + me) * SLAB_MAIL + q] = x;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < world) st_release_sys(slab_flags(p.mail[t], world) + SF_MAIL0 + me, v);
+}
+__global__ void k_mail_wait(double* mymail, int world, unsigned long long v) {
+  const int t = threadIdx.x;
+  if (t < world) while (ld_acquire_sys(slab_flags(mymail, world) + SF_MAIL0 + t) < v) {}
+}
+
+// what the ordered-sweep kernels need to talk to the neighbouring slabs
+struct SlabLink {
+  int on;                         // 0 = single GPU
+  int has_lo, has_hi, k0, np_glob, nz_lo;
+  unsigned long long* my_flags;   // my flag words (neighbours write SF_S_LO / SF_S_HI)
+  unsigned long long* lo_flags;   // lower neighbour's flag words (I write its SF_S_HI)
+  unsigned long long* hi_flags;   // upper neighbour's flag words (I write its SF_S_LO)
+  unsigned long long base;        // handshake counter value before this launch
+  unsigned long long* go;         // local release word for the extended barrier (zeroed by the host)
+};
+
+// z+ face coefficients of the lower halo plane (k = -1): the sweep kernel reads them as the z- coupling of the
+// bottom owned plane (c_f of the interface face, fluid.hpp:957-964); written straight into the sheared array
+template <int DIM>
+__global__ void k_cz_halo(Geo g, const double* __restrict__ dc, double* __restrict__ CZ) {
+  const long long nxy = (long long)g.n[0] * g.n[1];
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nxy) return;
+  const int i = (int)(t % g.n[0]), j = (int)(t / g.n[0]);
+  const long long cm = cidx(g, i, j, -1), cp = cidx(g, i, j, 0);
+  const bool inner = cell_ok(g, i, j, -1) && cell_ok(g, i, j, 0);
+  double cf = 0.;
+  if (inner) {
+    const double dfc = dc[cm] * (1. - 0.5) + dc[cp] * 0.5;
+    const double coeff = -g.area[2] / (g.h[2] * dfc);
+    cf = -coeff;
+  }
+  CZ[shidx(g, i, j, -1)] = cf;
+}

@@ -13,6 +13,7 @@
 #pragma once
 #include <cooperative_groups.h>
 #include "hg_device.cuh"
+#include "hg_slab.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -48,6 +49,37 @@ DV void grid_barrier(unsigned long long* bar, unsigned int nblocks, unsigned int
   ++epoch;
   __syncthreads();
 }
+// Barrier of a slab-decomposed sweep step: once all local CTAs have arrived, CTA 0 tells both neighbouring GPUs
+// "step base+epoch+1 done" (system-scope release store into their flag words, after the interface values
+// written into their halo planes), waits for the same from them, then releases the local CTAs.
+DV void grid_barrier(unsigned long long* bar, unsigned int nblocks, unsigned int& epoch, const SlabLink& L) {
+  if (!L.on) { grid_barrier(bar, nblocks, epoch); return; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long target = (unsigned long long)(epoch + 1u) * nblocks;
+    unsigned long long old, cur;
+    asm volatile("atom.add.release.gpu.global.u64 %0, [%1], 1;" : "=l"(old) : "l"(bar) : "memory");
+    if (blockIdx.x == 0) {
+      do {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(cur) : "l"(bar) : "memory");
+      } while (cur < target);
+      __threadfence_system();
+      const unsigned long long v = L.base + epoch + 1u;
+      if (L.has_lo) st_release_sys(L.lo_flags + SF_S_HI, v);
+      if (L.has_hi) st_release_sys(L.hi_flags + SF_S_LO, v);
+      if (L.has_lo) while (ld_acquire_sys(L.my_flags + SF_S_LO) < v) {}
+      if (L.has_hi) while (ld_acquire_sys(L.my_flags + SF_S_HI) < v) {}
+      asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(L.go), "l"((unsigned long long)(epoch + 1u)) : "memory");
+    } else {
+      do {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(cur) : "l"(L.go) : "memory");
+      } while (cur < (unsigned long long)(epoch + 1u));
+    }
+    __threadfence();
+  }
+  ++epoch;
+  __syncthreads();
+}
 
 // Hyperplane tiles.  A tile is SOLVER_BY consecutive rows j x SOLVER_BX consecutive i of one plane
 // k' = i+j+k; only tiles that contain at least one cell are listed (built once per mesh on the host).
@@ -68,19 +100,22 @@ DV bool tile_cell(const Geo& g, const TileTable& tt, int e, int kp, int& i, int&
 }
 // Tiles of step T for sweeps [smin, smax] (planes T-2s): flat id -> (plane, tile) by binary search in cum2
 struct StepTiles { int kp_lo, kp_hi, base, total; };
+// T is the LOCAL step (global step minus the slab's first plane k0); it may lie outside the local range
 DV StepTiles step_tiles(const Geo& g, const TileTable& tt, int T, int S) {
+  StepTiles st; st.kp_lo = st.kp_hi = 0; st.base = 0; st.total = 0;
+  if (T < 0) return st;
   int smin = 0; if (T - (g.np - 1) > 0) smin = (T - (g.np - 1) + 1) / 2;
   int smax = T / 2; if (smax > S - 1) smax = S - 1;
-  StepTiles st;
+  if (smax < smin) return st;
   st.kp_hi = T - 2 * smin; st.kp_lo = T - 2 * smax;
   st.base = st.kp_lo >= 2 ? tt.cum2[st.kp_lo - 2] : 0;
-  st.total = smax >= smin ? tt.cum2[st.kp_hi] - st.base : 0;
+  st.total = tt.cum2[st.kp_hi] - st.base;
   return st;
 }
 // Per step: sc[m] = number of tiles of the m+1 lowest active planes (inclusive running count), kept in
 // shared memory; a slot walks its ids in ascending order, so (plane, tile) follow by a two-pointer scan.
 DV void fill_step_table(const TileTable& tt, const StepTiles& st, int* sc) {
-  const int nact = ((st.kp_hi - st.kp_lo) >> 1) + 1;
+  const int nact = st.total > 0 ? ((st.kp_hi - st.kp_lo) >> 1) + 1 : 0;
   for (int t = threadIdx.x; t < nact; t += blockDim.x) sc[t] = tt.cum2[st.kp_lo + 2 * t] - st.base;
   __syncthreads();
 }
@@ -96,6 +131,8 @@ struct GsArgs {
   int s_begin, s_end;  // sweeps [s_begin, s_end) are run by this launch
   double omega;
   TileTable tt;
+  SlabLink link;       // neighbouring slabs (multi-GPU), link.on == 0 on a single GPU
+  double *PP_lo, *PP_hi;   // the neighbours' solution arrays (peer memory)
 };
 
 // Rows of the pressure-correction system (fluid.hpp:972-1014) are rebuilt on the fly from the three face
@@ -105,12 +142,17 @@ template <int DIM, bool EXCL>
 __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_gs_persistent(Geo g, GsArgs a) {
   __shared__ int sc[SOLVER_SC];
   const int S = a.s_end - a.s_begin;
-  const int Tmax = (g.np - 1) + 2 * (S - 1);
+  // slab decomposition: all ranks walk the GLOBAL hyperplane schedule; this rank's plane of sweep s at global
+  // step Tg is Tg - 2 s - k0
+  const SlabLink L = a.link;
+  const int Tmax = ((L.on ? L.np_glob : g.np) - 1) + 2 * (S - 1);
+  const int koff = L.on ? L.k0 : 0;
   const long long PS = (long long)g.n[1] * g.n[0];   // plane stride of the sheared layout
   const int nx = g.n[0];
   const int gslot = blockIdx.x * SOLVER_SLOTS + (threadIdx.x / SOLVER_TILE), nslots = gridDim.x * SOLVER_SLOTS;
   unsigned int epoch = 0;
-  for (int T = 0; T <= Tmax; ++T) {
+  for (int Tg = 0; Tg <= Tmax; ++Tg) {
+    const int T = Tg - koff;
     const StepTiles st = step_tiles(g, a.tt, T, S);
     fill_step_table(a.tt, st, sc);
     // contiguous id range per slot (neighbouring tiles share rows -> cache reuse); first plane by binary search
@@ -163,7 +205,12 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_gs_persistent(Geo g, GsAr
         }
         const double value = -(rhs + sum) / diag;
         const double corr = value - xold;
-        a.PP[cs] = xold + corr * a.omega;
+        const double xnew = xold + corr * a.omega;
+        a.PP[cs] = xnew;
+        if (L.on && DIM > 2) {   // interface cells: the new value is also the neighbour slab's halo value
+          if (k == g.n[2] - 1 && L.has_hi) { a.PP_hi[((long long)(i + j) * g.n[1] + j) * nx + i] = xnew; __threadfence_system(); }
+          if (k == 0 && L.has_lo) { a.PP_lo[((long long)(i + j + L.nz_lo + 1) * g.n[1] + j) * nx + i] = xnew; __threadfence_system(); }
+        }
         ac = fabs(corr);
         if (!(ac == ac)) ac = 0.;
       }
@@ -171,7 +218,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_gs_persistent(Geo g, GsAr
       ac = warp_max(ac);
       if ((threadIdx.x & 31) == 0 && ac > 0.) atomic_max_nonneg(&a.diff[a.s_begin + s], ac);
     }
-    grid_barrier(a.tt.bar, gridDim.x, epoch);
+    grid_barrier(a.tt.bar, gridDim.x, epoch, L);
   }
 }
 
@@ -182,15 +229,21 @@ struct LuArgs {
   double* X[3];         // sheared result
   int ncomp;
   TileTable tt;
+  SlabLink link;
+  double *X_lo[3], *X_hi[3];   // the neighbours' result arrays (peer memory)
 };
 template <int DIM>
 __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_lu_persistent(Geo g, LuArgs a) {
   const long long PS = (long long)g.n[1] * g.n[0];
   const int nx = g.n[0];
   const int gslot = blockIdx.x * SOLVER_SLOTS + (threadIdx.x / SOLVER_TILE), nslots = gridDim.x * SOLVER_SLOTS;
+  const SlabLink L = a.link;
+  const int npg = L.on ? L.np_glob : g.np, koff = L.on ? L.k0 : 0;
   unsigned int epoch = 0;
-  // forward step (linear.hpp:537-548)
-  for (int kp = 0; kp < g.np; ++kp) {
+  // forward step (linear.hpp:537-548); global planes in ascending order, this rank's plane is P - k0
+  for (int P = 0; P < npg; ++P) {
+    const int kp = P - koff;
+    if (kp >= 0 && kp < g.np)
     for (int e = a.tt.tileoff[kp] + gslot; e < a.tt.tileoff[kp + 1]; e += nslots) {
       int i, j, k;
       if (!tile_cell(g, a.tt, e, kp, i, j, k)) continue;
@@ -203,13 +256,17 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_lu_persistent(Geo g, LuAr
         if (zm) sum += azm * __ldcg(&a.X[n][cs - PS]);
         if (ym) sum += aym * __ldcg(&a.X[n][cs - PS - nx]);
         if (xm) sum += axm * __ldcg(&a.X[n][cs - PS - 1]);
-        a.X[n][cs] = (-a.R[n][cs] - sum) / diag;
+        const double xv = (-a.R[n][cs] - sum) / diag;
+        a.X[n][cs] = xv;
+        if (L.on && DIM > 2 && k == g.n[2] - 1 && L.has_hi) { a.X_hi[n][((long long)(i + j) * g.n[1] + j) * nx + i] = xv; __threadfence_system(); }
       }
     }
-    grid_barrier(a.tt.bar, gridDim.x, epoch);
+    grid_barrier(a.tt.bar, gridDim.x, epoch, L);
   }
   // backward step (linear.hpp:551-563)
-  for (int kp = g.np - 1; kp >= 0; --kp) {
+  for (int P = npg - 1; P >= 0; --P) {
+    const int kp = P - koff;
+    if (kp >= 0 && kp < g.np)
     for (int e = a.tt.tileoff[kp] + gslot; e < a.tt.tileoff[kp + 1]; e += nslots) {
       int i, j, k;
       if (!tile_cell(g, a.tt, e, kp, i, j, k)) continue;
@@ -222,10 +279,12 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_lu_persistent(Geo g, LuAr
         if (zp) sum += azp * __ldcg(&a.X[n][cs + PS]);
         if (yp) sum += ayp * __ldcg(&a.X[n][cs + PS + nx]);
         if (xp) sum += axp * __ldcg(&a.X[n][cs + PS + 1]);
-        a.X[n][cs] = __ldcg(&a.X[n][cs]) - sum / diag;
+        const double xv = __ldcg(&a.X[n][cs]) - sum / diag;
+        a.X[n][cs] = xv;
+        if (L.on && DIM > 2 && k == 0 && L.has_lo) { a.X_lo[n][((long long)(i + j + L.nz_lo + 1) * g.n[1] + j) * nx + i] = xv; __threadfence_system(); }
       }
     }
-    grid_barrier(a.tt.bar, gridDim.x, epoch);
+    grid_barrier(a.tt.bar, gridDim.x, epoch, L);
   }
 }
 
