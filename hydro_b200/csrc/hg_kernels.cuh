@@ -380,7 +380,8 @@ DV double face_coeff(const Geo& g, const double* __restrict__ dc, int d, const F
 // the sheared layout; the sweep kernels regenerate the off-diagonals A/(h d_f) from it.
 template <int DIM>
 __global__ void k_prhs(Geo g, const double* __restrict__ Fs, const double* __restrict__ dc, int out_sheared,
-                       double* __restrict__ RP, double* __restrict__ CX, double* __restrict__ CY, double* __restrict__ CZ) {
+                       double* __restrict__ RP, double* __restrict__ CX, double* __restrict__ CY, double* __restrict__ CZ,
+                       double* __restrict__ DG = nullptr) {
   CELL_LOOP_PROLOG(g)
   const long long cs = out_sheared ? shidx(g, i, j, k) : c;
   // face coefficients of the cell's plus faces for the sweep kernel (0 when the face is not inner)
@@ -390,6 +391,26 @@ __global__ void k_prhs(Geo g, const double* __restrict__ Fs, const double* __res
     for (int d = 0; d < DIM; ++d) {
       FaceInfo f = face_info<DIM>(g, d, i + (d == 0), j + (d == 1), k + (d == 2));
       if (f.type == FT_INNER) cf[d] = face_coeff<DIM>(g, dc, d, f);
+    }
+    if (DG) {
+      // k_gs_tiled: explicit diagonal = ordered sum over the faces x-,x+,y-,y+,z-,z+ (fluid.hpp:979-984; absent
+      // faces add 0), 1 for identity rows; the coefficients of the faces of the fixed-pressure cell are stored
+      // as 0 so that the terms removed by SetKnownValue (fluid.hpp:1010) vanish from the sums
+      double cm[3] = {0., 0., 0.};
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) {
+        FaceInfo f = face_info<DIM>(g, d, i, j, k);
+        if (f.type == FT_INNER) cm[d] = face_coeff<DIM>(g, dc, d, f);
+      }
+      double diag = cm[0] + cf[0]; diag = diag + cm[1]; diag = diag + cf[1];
+      if (DIM > 2) { diag = diag + cm[2]; diag = diag + cf[2]; }
+      const bool ident = c == g.pfix || cell_excl(g, i, j, k);
+      DG[cs] = ident ? 1. : diag;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) {
+        const long long nb = cidx(g, i + (d == 0), j + (d == 1), k + (d == 2));
+        if (c == g.pfix || nb == g.pfix) cf[d] = 0.;
+      }
     }
     CX[cs] = cf[0]; CY[cs] = cf[1]; if (DIM > 2) CZ[cs] = cf[2];
   }

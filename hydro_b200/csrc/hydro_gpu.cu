@@ -17,6 +17,7 @@
 #include "hg_kernels.cuh"
 #include "hg_solvers.cuh"
 #include "hg_slab.cuh"
+#include "hg_gs_tiled.cuh"
 
 enum { L_TC = 0, L_TP = 1, L_IC = 2, L_IP = 3 };
 
@@ -41,6 +42,13 @@ struct hg_state {
   double *An[10] = {};   // natural-layout staging of rows/constants before the shear transpose (3-D)
   double *A[7] = {}, *R[3] = {}, *X[3] = {}, *D = nullptr, *CYs = nullptr, *CZs = nullptr, *RP = nullptr, *PP = nullptr, *PPsave = nullptr;
   double* mailbox = nullptr; unsigned long long* xflags = nullptr;   // peer-written scratch (multi-GPU)
+  // time-skewed tile sweeps (hg_gs_tiled.cuh): explicit diagonal, task lists per number of sweeps in a launch
+  bool gs_tiled = false;
+  double* DGs = nullptr;
+  struct GtPlan { int ntasks = 0; GtTask* tasks = nullptr; int* progress = nullptr; };
+  std::map<int, GtPlan> gt_plans;
+  int* gt_ctl = nullptr;
+  int num_sms = 0;
   double* resid = nullptr;    // per-iteration convergence indicators of the current step (device, 4096)
   double* scal = nullptr;     // device scalars: [0] resid, [1] auto dt, [2..] stat (36), then diffs
   int* flag = nullptr;        // NaN flag
@@ -350,12 +358,80 @@ static int run_lu_relaxed(hg_state* s, const double* R, double* res, double* cor
   return 0;
 }
 
+// Task list of k_gs_tiled for a launch of S sweeps: boxes (I, J, group) sorted by I + J + 3 group, which puts every
+// dependency of a box before it (own group: (I-1,J), (I,J-1), (I-1,J-1); previous group: (I..I+1, J..J+1)).
+static int gt_plan(hg_state* s, int S, hg_state::GtPlan** out) {
+  auto it = s->gt_plans.find(S);
+  if (it != s->gt_plans.end()) { *out = &it->second; return 0; }
+  const int nx = s->n[0], ny = s->n[1], nz = s->n[2];
+  const int NG = (S + GT_B - 1) / GT_B, NI = (nx + GT_B - 1 + GT_TX - 1) / GT_TX, NJ = (ny + GT_B - 1 + GT_TY - 1) / GT_TY;
+  struct Key { int w, gI, J, I; };
+  std::vector<Key> keys;
+  auto nsw_of = [&](int gI) { return std::min(GT_B, S - gI * GT_B); };
+  auto exists = [&](int I, int J, int gI) {
+    if (I < 0 || J < 0 || gI < 0 || I >= NI || J >= NJ || gI >= NG) return false;
+    const int nsw = nsw_of(gI);
+    return I * GT_TX - (nsw - 1) < nx && J * GT_TY - (nsw - 1) < ny;
+  };
+  for (int gI = 0; gI < NG; ++gI) for (int J = 0; J < NJ; ++J) for (int I = 0; I < NI; ++I)
+    if (exists(I, J, gI)) keys.push_back({I + J + 3 * gI, gI, J, I});
+  std::stable_sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.w < b.w; });
+  std::vector<int> index((size_t)NG * NJ * NI, -1);
+  auto at = [&](int I, int J, int gI) -> int { return exists(I, J, gI) ? index[((size_t)gI * NJ + J) * NI + I] : -1; };
+  for (size_t q = 0; q < keys.size(); ++q) index[((size_t)keys[q].gI * NJ + keys[q].J) * NI + keys[q].I] = (int)q;
+  std::vector<GtTask> tasks(keys.size());
+  for (size_t q = 0; q < keys.size(); ++q) {
+    const Key& k = keys[q];
+    GtTask& t = tasks[q];
+    t.I0 = k.I * GT_TX; t.J0 = k.J * GT_TY; t.s0 = k.gI * GT_B; t.nsw = nsw_of(k.gI);
+    t.Tlo = std::max(0, t.I0 - (t.nsw - 1)) + std::max(0, t.J0 - (t.nsw - 1)) - 2;
+    t.Thi = std::min(nx - 1, t.I0 + GT_TX - 1) + std::min(ny - 1, t.J0 + GT_TY - 1) + (nz - 1) + 2 * (t.nsw - 1);
+    t.dep[0] = at(k.I - 1, k.J, k.gI); t.dep[1] = at(k.I, k.J - 1, k.gI); t.dep[2] = at(k.I - 1, k.J - 1, k.gI);
+    t.dep[3] = at(k.I, k.J, k.gI - 1); t.dep[4] = at(k.I + 1, k.J, k.gI - 1);
+    t.dep[5] = at(k.I, k.J + 1, k.gI - 1); t.dep[6] = at(k.I + 1, k.J + 1, k.gI - 1);
+    for (int d = 0; d < GT_MAXDEP; ++d) if (t.dep[d] >= (int)q) { s->err = "gt_plan: dependency order violated"; return HG_ERR_INVALID; }
+  }
+  hg_state::GtPlan pl;
+  pl.ntasks = (int)tasks.size();
+  if (dalloc(s, &pl.tasks, pl.ntasks, false) || dalloc(s, &pl.progress, pl.ntasks, true)) return HG_ERR_CUDA;
+  CK(cudaMemcpyAsync(pl.tasks, tasks.data(), tasks.size() * sizeof(GtTask), cudaMemcpyHostToDevice, s->st));
+  CK(cudaStreamSynchronize(s->st));   // `tasks` goes out of scope
+  s->gt_plans[S] = pl;
+  *out = &s->gt_plans[S];
+  return 0;
+}
+static int gt_launch(hg_state* s, int sb, int se, double omega) {
+  hg_state::GtPlan* pl = nullptr;
+  if (int rc = gt_plan(s, se - sb, &pl)) return rc;
+  GtArgs a; a.CX = s->D; a.CY = s->CYs; a.CZ = s->CZs; a.RP = s->RP; a.DG = s->DGs; a.PP = s->PP; a.diff = s->diffs;
+  a.s_begin = sb; a.omega = omega; a.tasks = pl->tasks; a.ntasks = pl->ntasks; a.progress = pl->progress; a.ctl = s->gt_ctl;
+  a.lag_prev = 2 * GT_B + 1;
+  CK(cudaMemsetAsync(pl->progress, 0, pl->ntasks * sizeof(int), s->st));
+  CK(cudaMemsetAsync(s->gt_ctl, 0, sizeof(int), s->st));   // next-task counter; the abort flag [1] is sticky
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (s->profile_on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s->st); }
+  const int grid = std::min(pl->ntasks, s->num_sms);
+  k_gs_tiled<<<grid, GT_THREADS, GT_SMEM_DOUBLES * sizeof(double), s->st>>>(s->geo, a);
+  CK(cudaGetLastError());
+  if (e0) { cudaEventRecord(e1, s->st); s->prof_ev[0].push_back({e0, e1}); }
+  ++s->launches;
+  return 0;
+}
+static int gt_check(hg_state* s) {   // after the sweeps: did a dependency wait time out?
+  int h = 0;
+  CK(cudaMemcpyAsync(&h, s->gt_ctl + 1, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+  CK(cudaStreamSynchronize(s->st));
+  if (h) { s->err = "k_gs_tiled: dependency wait timed out"; return HG_ERR_CUDA; }
+  return 0;
+}
+
 static int solve_pressure(hg_state* s) {
   const hg_config& c = s->cfg;
   int it = 0; double df = 0.;
   if (c.linear_solver_pressure == HG_LS_GAUSS_SEIDEL) {
     auto launch = [&](int sb, int se) -> int {
-      GsArgs a; a.CX = s->D; a.CY = s->CYs; a.CZ = s->CZs; a.RP = s->RP; a.PP = s->PP; a.diff = s->diffs; a.s_begin = sb; a.s_end = se;
+      if (s->gs_tiled) return gt_launch(s, sb, se, c.lu_relaxed_relaxation_factor);
+      GsArgs a{}; a.CX = s->D; a.CY = s->CYs; a.CZ = s->CZs; a.RP = s->RP; a.PP = s->PP; a.diff = s->diffs; a.s_begin = sb; a.s_end = se;
       a.omega = c.lu_relaxed_relaxation_factor; a.tt = s->tt;
       if (s->dim == 3) return s->any_excl ? coop_launch(s, k_gs_persistent<3, true>, s->grid_solver, s->geo, a, 0)
                                           : coop_launch(s, k_gs_persistent<3, false>, s->grid_solver, s->geo, a, 0);
@@ -363,6 +439,7 @@ static int solve_pressure(hg_state* s) {
                          : coop_launch(s, k_gs_persistent<2, false>, s->grid_solver, s->geo, a, 0);
     };
     if (int rc = run_sor(s, s->PP, s->nsh, c.lu_relaxed_tolerance, c.lu_relaxed_num_iters_limit, launch, &it, &df)) return rc;
+    if (s->gs_tiled) if (int rc = gt_check(s)) return rc;
     DIMSEL(s, k_pcorr, nblk(s->nc), 256, s->geo, s->PP, s->p[L_IP], c.pressure_relaxation_factor, s->pc, s->p[L_IC]);
   } else if (c.linear_solver_pressure == HG_LS_JACOBI) {
     // natural layout: constants back from the sheared array, rows regenerated from d_c
@@ -404,7 +481,7 @@ static int shear_arrays(hg_state* s, double* const* in, double* const* out, int 
 }
 
 static int solve_lu(hg_state* s, int ncomp) {
-  LuArgs a;
+  LuArgs a{};
   for (int t = 0; t < 7; ++t) a.A[t] = s->A[t];
   for (int n = 0; n < 3; ++n) { a.R[n] = s->R[n]; a.X[n] = s->X[n]; }
   a.ncomp = ncomp; a.tt = s->tt;
@@ -575,11 +652,11 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
   tpop(s);
   tpush(s, "fluid.5.pressure-system");
   if (s->dim == 3) {
-    DIMSEL(s, k_prhs, gb, 256, s->geo, s->Fs, s->dc, 0, s->An[0], s->An[1], s->An[2], s->An[3]);
-    double* outs[4] = {s->RP, s->D, s->CYs, s->CZs};
-    shear_arrays(s, s->An, outs, 4);
+    DIMSEL(s, k_prhs, gb, 256, s->geo, s->Fs, s->dc, 0, s->An[0], s->An[1], s->An[2], s->An[3], s->gs_tiled ? s->An[4] : nullptr);
+    double* outs[5] = {s->RP, s->D, s->CYs, s->CZs, s->DGs};
+    shear_arrays(s, s->An, outs, s->gs_tiled ? 5 : 4);
   } else {
-    DIMSEL(s, k_prhs, gb, 256, s->geo, s->Fs, s->dc, 1, s->RP, s->D, s->CYs, s->CZs);
+    DIMSEL(s, k_prhs, gb, 256, s->geo, s->Fs, s->dc, 1, s->RP, s->D, s->CYs, s->CZs, nullptr);
   }
   tpop(s);
   tpush(s, "fluid.6.pressure-solve");
@@ -886,6 +963,11 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     for (int n = 0; n < dim; ++n) { T.R[n] = take(s->nsh); T.X[n] = take(s->nsh); }
     T.D = take(s->nsh); T.CYs = take(s->nsh); T.CZs = take(dim > 2 ? s->nsh : 1); T.RP = take(s->nsh); T.PP = take(s->nsh); T.PPsave = take(s->nsh);
     T.scal = take(64); T.resid = take(4096);
+    // pressure sweeps: time-skewed tiles in 3-D on one GPU (HYDRO_GS_KERNEL=hyperplane keeps the pipelined
+    // hyperplane kernel, which is also what 2-D and the slab-decomposed runs use)
+    { const char* e = getenv("HYDRO_GS_KERNEL");
+      T.gs_tiled = dim == 3 && s->world == 1 && cfg->linear_solver_pressure == HG_LS_GAUSS_SEIDEL && !(e && !strcmp(e, "hyperplane")); }
+    if (T.gs_tiled) T.DGs = take(s->nsh);
     // buffers peers read or write: exchange staging (2 parities x 2 directions x SLAB_MAX_ARRAYS x HG_HALO planes),
     // mailbox (2 parities x world x SLAB_MAIL doubles) and flag words
     if (s->world > 1) {
@@ -908,6 +990,12 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
 
   // solver grids: persistent cooperative kernels, all CTAs co-resident
   cudaDeviceProp prop; cudaGetDeviceProperties(&prop, s->dev);
+  s->num_sms = prop.multiProcessorCount;
+  if (s->gs_tiled) {
+    if (dalloc(s, &s->gt_ctl, 4, true)) return fail_create(s, HG_ERR_CUDA, "allocation failed: " + s->err);
+    if (cudaFuncSetAttribute(k_gs_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GT_SMEM_DOUBLES * sizeof(double))) != cudaSuccess)
+      return fail_create(s, HG_ERR_CUDA, "k_gs_tiled: shared memory request rejected");
+  }
   int occ_gs = 0, occ_lu = 0;
   if (dim == 3) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gs, k_gs_persistent<3, true>, SOLVER_THREADS, 0);
