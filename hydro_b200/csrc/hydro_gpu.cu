@@ -411,7 +411,7 @@ static int gt_launch(hg_state* s, int sb, int se, double omega) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (s->profile_on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s->st); }
   const int grid = std::min(pl->ntasks, s->num_sms);
-  k_gs_tiled<<<grid, GT_THREADS, GT_SMEM_DOUBLES * sizeof(double), s->st>>>(s->geo, a);
+  k_gs_tiled<<<grid, GT_BLOCK, GT_SMEM_DOUBLES * sizeof(double), s->st>>>(s->geo, a);
   CK(cudaGetLastError());
   if (e0) { cudaEventRecord(e1, s->st); s->prof_ev[0].push_back({e0, e1}); }
   ++s->launches;
@@ -993,6 +993,9 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
   s->num_sms = prop.multiProcessorCount;
   if (s->gs_tiled) {
     if (dalloc(s, &s->gt_ctl, 4, true)) return fail_create(s, HG_ERR_CUDA, "allocation failed: " + s->err);
+    // entry 0 of the sheared arrays (unused corner of the lower halo plane) is what threads without a cell read:
+    // zero coefficients (set by the allocation), unit diagonal
+    { const double one = 1.; cudaMemcpyAsync(s->DGs, &one, sizeof(double), cudaMemcpyHostToDevice, s->st); cudaStreamSynchronize(s->st); }
     if (cudaFuncSetAttribute(k_gs_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GT_SMEM_DOUBLES * sizeof(double))) != cudaSuccess)
       return fail_create(s, HG_ERR_CUDA, "k_gs_tiled: shared memory request rejected");
   }
