@@ -358,8 +358,9 @@ static int run_lu_relaxed(hg_state* s, const double* R, double* res, double* cor
   return 0;
 }
 
-// Task list of k_gs_tiled for a launch of S sweeps: boxes (I, J, group) sorted by I + J + 3 group, which puts every
-// dependency of a box before it (own group: (I-1,J), (I,J-1), (I-1,J-1); previous group: (I..I+1, J..J+1)).
+// Task list of k_gs_tiled for a launch of S sweeps: boxes (I, J, group) sorted by the step at which they can start,
+// 32 I + 15 J + 65 group (a box starts 32 / 15 steps after its left / lower neighbour and 2B+1 steps after the box
+// (I+1, J+1) of the previous group), which also puts every dependency of a box before it (own group: (I-1,J), (I,J-1), (I-1,J-1); previous group: (I..I+1, J..J+1)).
 static int gt_plan(hg_state* s, int S, hg_state::GtPlan** out) {
   auto it = s->gt_plans.find(S);
   if (it != s->gt_plans.end()) { *out = &it->second; return 0; }
@@ -374,7 +375,7 @@ static int gt_plan(hg_state* s, int S, hg_state::GtPlan** out) {
     return I * GT_TX - (nsw - 1) < nx && J * GT_TY - (nsw - 1) < ny;
   };
   for (int gI = 0; gI < NG; ++gI) for (int J = 0; J < NJ; ++J) for (int I = 0; I < NI; ++I)
-    if (exists(I, J, gI)) keys.push_back({I + J + 3 * gI, gI, J, I});
+    if (exists(I, J, gI)) keys.push_back({GT_TX * I + GT_TY * J + (GT_TX + GT_TY + 2 * GT_B + 2) * gI, gI, J, I});
   std::stable_sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.w < b.w; });
   std::vector<int> index((size_t)NG * NJ * NI, -1);
   auto at = [&](int I, int J, int gI) -> int { return exists(I, J, gI) ? index[((size_t)gI * NJ + J) * NI + I] : -1; };
@@ -406,6 +407,7 @@ static int gt_launch(hg_state* s, int sb, int se, double omega) {
   GtArgs a; a.CX = s->D; a.CY = s->CYs; a.CZ = s->CZs; a.RP = s->RP; a.DG = s->DGs; a.PP = s->PP; a.diff = s->diffs;
   a.s_begin = sb; a.omega = omega; a.tasks = pl->tasks; a.ntasks = pl->ntasks; a.progress = pl->progress; a.ctl = s->gt_ctl;
   a.lag_prev = 2 * GT_B + 1;
+  a.PS8 = 8LL * s->n[0] * s->n[1]; a.DSH8 = 8LL * (2LL * s->n[0] * s->n[1] + s->n[0] + 1);
   CK(cudaMemsetAsync(pl->progress, 0, pl->ntasks * sizeof(int), s->st));
   CK(cudaMemsetAsync(s->gt_ctl, 0, sizeof(int), s->st));   // next-task counter; the abort flag [1] is sticky
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -961,12 +963,19 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     for (int q = 0; q < 7; ++q) T.A[q] = take(s->nsh);
     if (dim == 3) for (int q = 0; q < 10; ++q) T.An[q] = cells();
     for (int n = 0; n < dim; ++n) { T.R[n] = take(s->nsh); T.X[n] = take(s->nsh); }
-    T.D = take(s->nsh); T.CYs = take(s->nsh); T.CZs = take(dim > 2 ? s->nsh : 1); T.RP = take(s->nsh); T.PP = take(s->nsh); T.PPsave = take(s->nsh);
+    // the tile sweeps read a few hyperplanes beyond both ends of the solution and of the x+/y+ coefficient arrays:
+    // GT_PAD zero hyperplanes around them (never written)
+    const long long padn = (dim == 3 && s->world == 1) ? (long long)GT_PAD * s->nxy : 0;
+    auto take_padded = [&](long long n) -> double* { double* q = take(n + 2 * padn); return q ? q + padn : nullptr; };
+    T.D = take_padded(s->nsh); T.CYs = take_padded(s->nsh); T.CZs = take(dim > 2 ? s->nsh : 1); T.RP = take(s->nsh);
+    T.PP = take_padded(s->nsh); T.PPsave = take(s->nsh);
     T.scal = take(64); T.resid = take(4096);
     // pressure sweeps: time-skewed tiles in 3-D on one GPU (HYDRO_GS_KERNEL=hyperplane keeps the pipelined
     // hyperplane kernel, which is also what 2-D and the slab-decomposed runs use)
     { const char* e = getenv("HYDRO_GS_KERNEL");
-      T.gs_tiled = dim == 3 && s->world == 1 && cfg->linear_solver_pressure == HG_LS_GAUSS_SEIDEL && !(e && !strcmp(e, "hyperplane")); }
+      T.gs_tiled = dim == 3 && s->world == 1 && cfg->linear_solver_pressure == HG_LS_GAUSS_SEIDEL && !(e && !strcmp(e, "hyperplane")) &&
+                   8LL * (GT_PAD + 2) * s->nxy < (1LL << 31);   // 32-bit byte offsets inside k_gs_tiled
+    }
     if (T.gs_tiled) T.DGs = take(s->nsh);
     // buffers peers read or write: exchange staging (2 parities x 2 directions x SLAB_MAX_ARRAYS x HG_HALO planes),
     // mailbox (2 parities x world x SLAB_MAIL doubles) and flag words
