@@ -26,6 +26,7 @@ SYMBOLS = [
     "hg_update_properties", "hg_calc_stat", "hg_interp_grad", "hg_linear_solve", "hg_smooth_field",
     "hg_timers", "hg_timers_enable", "hg_launch_count", "hg_device_synchronize", "hg_event_record",
     "hg_event_elapsed_ms", "hg_profile_enable", "hg_profile_read",
+    "hg_ipc_record_size", "hg_ipc_export", "hg_ipc_import", "hg_link_local",
 ]
 
 
@@ -70,6 +71,11 @@ def load_library():
     l.hg_event_elapsed_ms.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
     l.hg_profile_enable.argtypes = [C.c_void_p, C.c_int]
     l.hg_profile_read.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), dp]
+    l.hg_ipc_record_size.argtypes = []
+    l.hg_ipc_record_size.restype = C.c_size_t
+    l.hg_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    l.hg_ipc_import.argtypes = [C.c_void_p, C.c_void_p]
+    l.hg_link_local.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     l.hg_launch_count.argtypes = [C.c_void_p]
     l.hg_launch_count.restype = C.c_longlong
     _lib = l
@@ -83,10 +89,13 @@ def _dptr(a):
 class Hydro:
     """Device-resident experiment; same surface as tests/oracle_api.Oracle."""
 
-    def __init__(self, params, device=0):
+    def __init__(self, params, device=0, world_size=1, rank=0, solver_ctas=0):
+        """world_size > 1: this handle owns z-slab `rank` (hydro_b200.parallel.slab_range); the ranks must be
+        linked (link_ipc / link_local, collective) before anything else is called."""
         self.l = load_library()
         self.params = params if isinstance(params, Params) else Params(params)
-        self.cfg = self.params.to_struct(device=device)
+        self.world_size, self.rank = world_size, rank
+        self.cfg = self.params.to_struct(device=device, world_size=world_size, rank=rank, solver_ctas=solver_ctas)
         h = C.c_void_p()
         rc = self.l.hg_create(C.byref(self.cfg), C.byref(h))
         if rc != 0:
@@ -96,6 +105,27 @@ class Hydro:
         self.nc = self.l.hg_num_cells(h)
         self.nf = self.l.hg_num_faces(h)
         self._res = []
+
+    # -- slab decomposition ---------------------------------------------------
+    def link_ipc(self, dist):
+        """Separate processes (one per GPU): all-gather the CUDA IPC records through torch.distributed, import."""
+        import torch
+        n = self.l.hg_ipc_record_size()
+        rec = (C.c_ubyte * n)()
+        self._chk(self.l.hg_ipc_export(self.h, rec, n))
+        mine = torch.frombuffer(bytearray(rec), dtype=torch.uint8).clone()
+        if dist.get_backend() == "nccl":
+            mine = mine.cuda()
+        parts = [torch.empty_like(mine) for _ in range(self.world_size)]
+        dist.all_gather(parts, mine)
+        blob = b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts)
+        buf = C.create_string_buffer(blob, len(blob))
+        self._chk(self.l.hg_ipc_import(self.h, buf))
+
+    def link_local(self, handles):
+        """Ranks living in this process (one thread each): `handles` = all Hydro objects in rank order."""
+        arr = (C.c_void_p * len(handles))(*[h.h.value for h in handles])
+        self._chk(self.l.hg_link_local(self.h, arr))
 
     def close(self):
         if getattr(self, "h", None):

@@ -52,7 +52,7 @@ class HgConfig(C.Structure):
         ("heat_relaxation_factor", C.c_double), ("time_second_order_heat", C.c_int),
         ("world_size", C.c_int), ("rank", C.c_int), ("device", C.c_int),
         ("nccl_unique_id", C.c_void_p),
-        ("pressure_sweeps_per_check", C.c_int), ("reserved", C.c_int * 7),
+        ("pressure_sweeps_per_check", C.c_int), ("solver_ctas", C.c_int), ("reserved", C.c_int * 6),
     ]
 
 
@@ -442,7 +442,7 @@ class Params(dict):
         return self
 
     # -- struct -----------------------------------------------------------------
-    def to_struct(self, world_size=1, rank=0, device=0, nccl_unique_id=None):
+    def to_struct(self, world_size=1, rank=0, device=0, nccl_unique_id=None, solver_ctas=0):
         p = self
 
         def need(k):
@@ -508,6 +508,7 @@ class Params(dict):
             self._uid_buf = C.create_string_buffer(bytes(nccl_unique_id), 128)
             c.nccl_unique_id = C.cast(self._uid_buf, C.c_void_p)
         c.pressure_sweeps_per_check = int(p.get("pressure_sweeps_per_check", 0))
+        c.solver_ctas = int(solver_ctas)
         return c
 
     def hydroconf_lines(self):

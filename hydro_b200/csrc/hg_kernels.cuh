@@ -36,6 +36,7 @@ __global__ void k_start_layer(double* __restrict__ ic, const double* __restrict_
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) ic[t] = tc[t] + (tc[t] - tp[t]) * ge;
 }
+__global__ void k_flag_to_double(const int* flag, double* out) { *out = *flag ? 1. : 0.; }
 // IsNan scan (solver.hpp:17-30): sets *flag when !(a*0 == 0)
 __global__ void k_nan_flag(const double* __restrict__ a, long long n, int* flag) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;

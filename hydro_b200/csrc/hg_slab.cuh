@@ -22,7 +22,7 @@ constexpr int SLAB_MAX_ARRAYS = 16;
 constexpr int SLAB_MAIL = 1056;      // doubles per rank per mailbox round (per-sweep norms of a 1024-sweep chunk fit)
 constexpr int SLAB_MAX_WORLD = 56;
 // flag words (unsigned long long) stored after the mailbox doubles
-enum { SF_X_LO = 0, SF_X_HI = 1, SF_S_LO = 2, SF_S_HI = 3, SF_MAIL0 = 8 };
+enum { SF_X_LO = 0, SF_X_HI = 1, SF_S_LO = 2, SF_S_HI = 3, SF_ERR = 6, SF_MAIL0 = 8 };
 
 struct Slab {
   int world = 1, rank = 0, has_lo = 0, has_hi = 0;
@@ -49,6 +49,18 @@ DV unsigned long long ld_acquire_sys(const unsigned long long* p) {
 }
 DV void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+// Bounded wait for a peer's flag (about 4 s): a rank that died or a protocol bug must not hang the device.  On
+// time-out the local error word is raised (the host reports it at the next reduction) and the caller goes on.
+DV void slab_wait(const unsigned long long* flag, unsigned long long v, unsigned long long* err) {
+  long long t0 = 0;
+  for (unsigned spins = 0; ld_acquire_sys(flag) < v; ++spins) {
+    if ((spins & 0x3ff) == 0x3ff) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 8000000000LL || *(volatile unsigned long long*)err) { *(volatile unsigned long long*)err = 1ull; return; }
+    }
+  }
 }
 
 struct PackArgs { const double* src[SLAB_MAX_ARRAYS]; int n, planes; };
@@ -80,14 +92,13 @@ __global__ void k_slab_signal(unsigned long long* flag_in_lower, unsigned long l
   if (flag_in_upper) st_release_sys(flag_in_upper, v);
 }
 
-// wait for the neighbours' flags, then pull their staged planes into my halo planes
-__global__ void k_slab_unpack(Geo g, UnpackArgs a, const double* xbuf_lo, const double* xbuf_hi, int parity,
-                              const unsigned long long* myflags, unsigned long long v) {
-  if (threadIdx.x == 0) {
-    if (xbuf_lo) while (ld_acquire_sys(&myflags[SF_X_LO]) < v) {}
-    if (xbuf_hi) while (ld_acquire_sys(&myflags[SF_X_HI]) < v) {}
-  }
-  __syncthreads();
+// wait for the neighbours' flags (one thread: a spinning grid could starve a peer that shares the device) ...
+__global__ void k_slab_wait(int has_lo, int has_hi, unsigned long long* myflags, unsigned long long v) {
+  if (has_lo) slab_wait(&myflags[SF_X_LO], v, &myflags[SF_ERR]);
+  if (has_hi) slab_wait(&myflags[SF_X_HI], v, &myflags[SF_ERR]);
+}
+// ... then pull their staged planes into my halo planes
+__global__ void k_slab_unpack(Geo g, UnpackArgs a, const double* xbuf_lo, const double* xbuf_hi, int parity) {
   const long long nxy = (long long)g.n[0] * g.n[1];
   const long long per = (long long)a.planes * nxy;
   const long long total = per * a.n;
@@ -117,7 +128,7 @@ __global__ void k_mail_post(MailPeers p, const double* __restrict__ vals, int n,
 }
 __global__ void k_mail_wait(double* mymail, int world, unsigned long long v) {
   const int t = threadIdx.x;
-  if (t < world) while (ld_acquire_sys(slab_flags(mymail, world) + SF_MAIL0 + t) < v) {}
+  if (t < world) slab_wait(slab_flags(mymail, world) + SF_MAIL0 + t, v, slab_flags(mymail, world) + SF_ERR);
 }
 
 // what the ordered-sweep kernels need to talk to the neighbouring slabs

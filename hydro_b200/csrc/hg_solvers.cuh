@@ -59,6 +59,7 @@ DV void grid_barrier(unsigned long long* bar, unsigned int nblocks, unsigned int
     const unsigned long long target = (unsigned long long)(epoch + 1u) * nblocks;
     unsigned long long old, cur;
     asm volatile("atom.add.release.gpu.global.u64 %0, [%1], 1;" : "=l"(old) : "l"(bar) : "memory");
+    (void)old;
     if (blockIdx.x == 0) {
       do {
         asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(cur) : "l"(bar) : "memory");
@@ -67,8 +68,8 @@ DV void grid_barrier(unsigned long long* bar, unsigned int nblocks, unsigned int
       const unsigned long long v = L.base + epoch + 1u;
       if (L.has_lo) st_release_sys(L.lo_flags + SF_S_HI, v);
       if (L.has_hi) st_release_sys(L.hi_flags + SF_S_LO, v);
-      if (L.has_lo) while (ld_acquire_sys(L.my_flags + SF_S_LO) < v) {}
-      if (L.has_hi) while (ld_acquire_sys(L.my_flags + SF_S_HI) < v) {}
+      if (L.has_lo) slab_wait(L.my_flags + SF_S_LO, v, L.my_flags + SF_ERR);
+      if (L.has_hi) slab_wait(L.my_flags + SF_S_HI, v, L.my_flags + SF_ERR);
       asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(L.go), "l"((unsigned long long)(epoch + 1u)) : "memory");
     } else {
       do {

@@ -74,6 +74,8 @@ struct hg_state {
   int world = 1, rank = 0, k0 = 0, k1 = 0, nzg = 1;
   long long nxy = 0, ncg = 0;
   Slab slab;
+  bool initialised = false;
+  std::vector<void*> ipc_opened;
   bool profile_on = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[2];   // [0] pressure sweeps kernel, [1] lu kernel
   cudaEvent_t user_ev[8] = {};
@@ -81,6 +83,8 @@ struct hg_state {
 };
 
 static thread_local std::string g_create_err;
+static const bool g_trace = getenv("HYDRO_SLAB_TRACE") != nullptr;
+#define TRACE(...) do { if (g_trace) { fprintf(stderr, __VA_ARGS__); fflush(stderr); } } while (0)
 
 #define CK(call)                                                                   \
   do {                                                                             \
@@ -138,6 +142,7 @@ static int slab_exchange(hg_state* s, double* const* arrs, int n, int planes) {
   Slab& sl = s->slab;
   const unsigned long long v = ++sl.xseq;
   const int parity = (int)(v & 1ull);
+  TRACE("[r%d] exchange %llu arrays %d planes %d\n", s->rank, v, n, planes);
   PackArgs pa; UnpackArgs ua; pa.n = ua.n = n; pa.planes = ua.planes = planes;
   for (int q = 0; q < n; ++q) { pa.src[q] = arrs[q]; ua.dst[q] = arrs[q]; }
   const long long total = (long long)n * planes * s->nxy;
@@ -146,9 +151,9 @@ static int slab_exchange(hg_state* s, double* const* arrs, int n, int planes) {
   unsigned long long* f_lo = sl.has_lo ? slab_flags(sl.mail_peer[s->rank - 1], s->world) + SF_X_HI : nullptr;
   unsigned long long* f_hi = sl.has_hi ? slab_flags(sl.mail_peer[s->rank + 1], s->world) + SF_X_LO : nullptr;
   k_slab_signal<<<1, 1, 0, s->st>>>(f_lo, f_hi, v);
-  k_slab_unpack<<<blocks, 256, 0, s->st>>>(s->geo, ua, sl.has_lo ? sl.xbuf_lo : nullptr, sl.has_hi ? sl.xbuf_hi : nullptr, parity,
-                                           slab_flags(sl.mail, s->world), v);
-  s->launches += 3;
+  k_slab_wait<<<1, 1, 0, s->st>>>(sl.has_lo, sl.has_hi, slab_flags(sl.mail, s->world), v);
+  k_slab_unpack<<<blocks, 256, 0, s->st>>>(s->geo, ua, sl.has_lo ? sl.xbuf_lo : nullptr, sl.has_hi ? sl.xbuf_hi : nullptr, parity);
+  s->launches += 4;
   return 0;
 }
 static int slab_exchange(hg_state* s, std::initializer_list<double*> arrs, int planes) {
@@ -169,6 +174,7 @@ static int slab_gather(hg_state* s, const double* dev_vals, int n, std::vector<d
   Slab& sl = s->slab;
   const unsigned long long v = ++sl.mseq;
   const int parity = (int)(v & 1ull);
+  TRACE("[r%d] gather %llu n %d\n", s->rank, v, n);
   MailPeers mp; for (int r = 0; r < s->world; ++r) mp.mail[r] = sl.mail_peer[r];
   k_mail_post<<<1, 1024, 0, s->st>>>(mp, dev_vals, n, parity, s->rank, s->world, v);
   k_mail_wait<<<1, 64, 0, s->st>>>(sl.mail, s->world, v);
@@ -176,9 +182,36 @@ static int slab_gather(hg_state* s, const double* dev_vals, int n, std::vector<d
   for (int r = 0; r < s->world; ++r)
     CK(cudaMemcpyAsync(out.data() + (size_t)r * n, sl.mail + ((long long)parity * s->world + r) * SLAB_MAIL, n * sizeof(double),
                        cudaMemcpyDeviceToHost, s->st));
+  unsigned long long perr = 0;
+  CK(cudaMemcpyAsync(&perr, slab_flags(sl.mail, s->world) + SF_ERR, sizeof perr, cudaMemcpyDeviceToHost, s->st));
   CK(cudaStreamSynchronize(s->st));
+  TRACE("[r%d] gather %llu done err %llu\n", s->rank, v, perr);
+  if (perr) { s->err = "slab decomposition: a wait for a neighbouring rank timed out"; return HG_ERR_CUDA; }
   return 0;
 }
+// reduction of n device doubles over the ranks, done on the host in rank order (identical on every rank);
+// op: 0 = max, 1 = min, 2 = sum.  Result in host memory `out`.
+static int slab_reduce(hg_state* s, const double* dev_vals, int n, int op, double* out) {
+  std::vector<double> all;
+  if (int rc = slab_gather(s, dev_vals, n, all)) return rc;
+  for (int q = 0; q < n; ++q) {
+    double v = all[q];
+    for (int r = 1; r < s->world; ++r) {
+      const double w = all[(size_t)r * n + q];
+      v = op == 0 ? (v < w ? w : v) : op == 1 ? (w < v ? w : v) : v + w;
+    }
+    out[q] = v;
+  }
+  return 0;
+}
+// all ranks have executed everything enqueued so far (no-op on one GPU)
+static int slab_sync(hg_state* s) {
+  if (s->world <= 1) return 0;
+  double dummy[1];
+  return slab_reduce(s, s->scal + 60, 1, 0, dummy);
+}
+#define XCH(s, planes, ...) \
+  do { if ((s)->world > 1) { if (int rc_ = slab_exchange((s), {__VA_ARGS__}, (planes))) return rc_; } } while (0)
 static SlabLink slab_link(hg_state* s, unsigned long long nbarriers) {
   SlabLink L; memset(&L, 0, sizeof L);
   if (s->world <= 1) return L;
@@ -188,6 +221,7 @@ static SlabLink slab_link(hg_state* s, unsigned long long nbarriers) {
   L.lo_flags = sl.has_lo ? slab_flags(sl.mail_peer[s->rank - 1], s->world) : nullptr;
   L.hi_flags = sl.has_hi ? slab_flags(sl.mail_peer[s->rank + 1], s->world) : nullptr;
   L.base = sl.hseq; sl.hseq += nbarriers;
+  TRACE("[r%d] solver link base %llu barriers %llu\n", s->rank, L.base, nbarriers);
   L.go = s->tt.bar + 3;
   return L;
 }
@@ -216,7 +250,11 @@ static int coop_launch(hg_state* s, K kern, int grid, Geo g, A args, int prof_sl
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   CK(cudaMemsetAsync(s->tt.bar, 0, 4 * sizeof(unsigned long long), s->st));   // barrier arrival counter + release word
   if (s->profile_on && prof_slot >= 0) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s->st); }
-  CK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(SOLVER_THREADS), params, 0, s->st));
+  // Cooperative launch = guaranteed co-residency of the grid (the kernels use their own grid barrier).  Ranks that
+  // share a device (solver_ctas > 0, tests) launch normally: two cooperative grids are not run side by side, and
+  // the limited grids fit next to each other.
+  if (s->cfg.solver_ctas > 0) { CK(cudaLaunchKernel((void*)kern, dim3(grid), dim3(SOLVER_THREADS), params, 0, s->st)); }
+  else CK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(SOLVER_THREADS), params, 0, s->st));
   if (e0) { cudaEventRecord(e1, s->st); s->prof_ev[prof_slot].push_back({e0, e1}); }
   ++s->launches;
   return 0;
@@ -241,17 +279,23 @@ static int run_sor(hg_state* s, double* x, long long nx_, double tol, int limit,
   if (int rc = ensure_sweep_capacity(s, max_total)) return rc;
   CK(cudaMemsetAsync(x, 0, nx_ * sizeof(double), s->st));
   CK(cudaMemsetAsync(s->diffs, 0, max_total * sizeof(double), s->st));
+  // slabs: a neighbour's first sweep step stores into this rank's halo plane of x; it must not start before
+  // the reset above has been executed here
+  if (int rc = slab_sync(s)) return rc;
   if (!(tol > 0.)) {
     // `diff > tol` only fails for diff == 0 (or NaN): run all limit+1 sweeps, inspect the history once
-    for (int sb = 0; sb < max_total; sb += SOLVER_SC) if (int rc = launch(sb, std::min(sb + SOLVER_SC, max_total))) return rc;
-    CK(cudaMemcpyAsync(s->hdiffs, s->diffs, max_total * sizeof(double), cudaMemcpyDeviceToHost, s->st));
-    CK(cudaStreamSynchronize(s->st));
+    for (int sb = 0; sb < max_total; sb += SOLVER_SC) {
+      const int se = std::min(sb + SOLVER_SC, max_total);
+      if (int rc = launch(sb, se)) return rc;
+      if (int rc = slab_reduce(s, s->diffs + sb, se - sb, 0, s->hdiffs + sb)) return rc;
+    }
     int stop = -1;
     for (int k = 0; k < max_total; ++k) if (!(s->hdiffs[k] > tol)) { stop = k; break; }
     if (stop >= 0 && stop < max_total - 1) {   // stopped early: redo with the exact sweep count
       const double dstop = s->hdiffs[stop];
       CK(cudaMemsetAsync(x, 0, nx_ * sizeof(double), s->st));
       CK(cudaMemsetAsync(s->diffs, 0, max_total * sizeof(double), s->st));
+      if (int rc = slab_sync(s)) return rc;
       for (int sb = 0; sb < stop + 1; sb += SOLVER_SC) if (int rc = launch(sb, std::min(sb + SOLVER_SC, stop + 1))) return rc;
       *out_iter = stop; *out_diff = dstop;
       return 0;
@@ -267,13 +311,14 @@ static int run_sor(hg_state* s, double* x, long long nx_, double tol, int limit,
     int n = std::min(chunk, max_total - done);
     CK(cudaMemcpyAsync(s->PPsave, x, nx_ * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
     if (int rc = launch(done, done + n)) return rc;
-    CK(cudaMemcpyAsync(s->hdiffs + done, s->diffs + done, n * sizeof(double), cudaMemcpyDeviceToHost, s->st));
-    CK(cudaStreamSynchronize(s->st));
+    if (int rc = slab_reduce(s, s->diffs + done, n, 0, s->hdiffs + done)) return rc;
     int stop = -1;
     for (int k = done; k < done + n; ++k) if (!(s->hdiffs[k] > tol)) { stop = k; break; }
     if (stop >= 0) {
       if (stop != done + n - 1) {
         CK(cudaMemcpyAsync(x, s->PPsave, nx_ * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
+        CK(cudaMemsetAsync(s->diffs + done, 0, n * sizeof(double), s->st));
+        if (int rc = slab_sync(s)) return rc;
         if (int rc = launch(done, stop + 1)) return rc;
       }
       *out_iter = stop; *out_diff = s->hdiffs[stop];
@@ -435,6 +480,10 @@ static int solve_pressure(hg_state* s) {
       if (s->gs_tiled) return gt_launch(s, sb, se, c.lu_relaxed_relaxation_factor);
       GsArgs a{}; a.CX = s->D; a.CY = s->CYs; a.CZ = s->CZs; a.RP = s->RP; a.PP = s->PP; a.diff = s->diffs; a.s_begin = sb; a.s_end = se;
       a.omega = c.lu_relaxed_relaxation_factor; a.tt = s->tt;
+      if (s->world > 1) {   // one neighbour handshake per global hyperplane step
+        a.link = slab_link(s, (unsigned long long)(s->slab.np_glob + 2 * (se - sb - 1)));
+        a.PP_lo = s->slab.PP_lo; a.PP_hi = s->slab.PP_hi;
+      }
       if (s->dim == 3) return s->any_excl ? coop_launch(s, k_gs_persistent<3, true>, s->grid_solver, s->geo, a, 0)
                                           : coop_launch(s, k_gs_persistent<3, false>, s->grid_solver, s->geo, a, 0);
       return s->any_excl ? coop_launch(s, k_gs_persistent<2, true>, s->grid_solver, s->geo, a, 0)
@@ -487,6 +536,10 @@ static int solve_lu(hg_state* s, int ncomp) {
   for (int t = 0; t < 7; ++t) a.A[t] = s->A[t];
   for (int n = 0; n < 3; ++n) { a.R[n] = s->R[n]; a.X[n] = s->X[n]; }
   a.ncomp = ncomp; a.tt = s->tt;
+  if (s->world > 1) {
+    a.link = slab_link(s, 2ull * s->slab.np_glob);
+    for (int n = 0; n < 3; ++n) { a.X_lo[n] = s->slab.X_lo[n]; a.X_hi[n] = s->slab.X_hi[n]; }
+  }
   if (s->dim == 3) return coop_launch(s, k_lu_persistent<3>, s->grid_lu, s->geo, a, 1);
   return coop_launch(s, k_lu_persistent<2>, s->grid_lu, s->geo, a, 1);
 }
@@ -499,6 +552,7 @@ static int smooth_field(hg_state* s, const double* in, int repeat, double* out) 
   double* bufs[2] = {(repeat % 2) ? out : s->w2, (repeat % 2) ? s->w2 : out};
   for (int r = 0; r < repeat; ++r) {
     double* dst = bufs[r % 2];
+    XCH(s, 1, const_cast<double*>(src));
     DIMSEL(s, k_smooth, nblk(s->nc), 256, s->geo, src, dst);
     src = dst;
   }
@@ -533,6 +587,8 @@ extern "C" int hg_update_properties(hg_handle s) {
       CK(cudaMemcpyAsync(s->force[d], s->w1, s->nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
     }
   }
+  // slabs: face values of density, viscosity and force are taken across the slab interfaces
+  XCH(s, 1, s->rho, s->mu, s->force[0], s->force[1], s->dim > 2 ? s->force[2] : nullptr);
   tpop(s);
   return 0;
 }
@@ -549,8 +605,21 @@ extern "C" int hg_calc_stat(hg_handle s, hg_step_stats* st) {
   for (int d = 0; d < 3; ++d) a.u[d] = s->u[L_TC][d] ? s->u[L_TC][d] : s->zero;
   a.out = s->scal + 2;
   DIMSEL(s, k_stat, nblk(s->nc), 256, s->geo, a);
-  CK(cudaMemcpyAsync(s->hscal + 2, s->scal + 2, 36 * sizeof(double), cudaMemcpyDeviceToHost, s->st));
-  CK(cudaStreamSynchronize(s->st));
+  if (s->world > 1) {   // sums in rank order; minima / maxima
+    std::vector<double> all;
+    if (int rc = slab_gather(s, s->scal + 2, 36, all)) return rc;
+    for (int q = 0; q < 36; ++q) {
+      double v = all[q];
+      for (int r = 1; r < s->world; ++r) {
+        const double w = all[(size_t)r * 36 + q];
+        v = (q % 12 == 7) ? (w < v ? w : v) : (q % 12 == 8) ? (v < w ? w : v) : v + w;
+      }
+      s->hscal[2 + q] = v;
+    }
+  } else {
+    CK(cudaMemcpyAsync(s->hscal + 2, s->scal + 2, 36 * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    CK(cudaStreamSynchronize(s->st));
+  }
   hg_step_stats& o = s->stat;
   for (int p = 0; p < c.num_phases; ++p) {
     const double* r = s->hscal + 2 + p * 12;
@@ -575,8 +644,15 @@ static int check_nan(hg_state* s, const double* a, long long n, const char* msg)
   CK(cudaMemsetAsync(s->flag, 0, sizeof(int), s->st));
   LAUNCH(s, k_nan_flag, nblk(n), 256, a, n, s->flag);
   int h = 0;
-  CK(cudaMemcpyAsync(&h, s->flag, sizeof(int), cudaMemcpyDeviceToHost, s->st));
-  CK(cudaStreamSynchronize(s->st));
+  if (s->world > 1) {   // every rank must take the same branch
+    LAUNCH(s, k_flag_to_double, 1, 1, s->flag, s->scal + 61);
+    double any = 0.;
+    if (int rc = slab_reduce(s, s->scal + 61, 1, 0, &any)) return rc;
+    h = any != 0.;
+  } else {
+    CK(cudaMemcpyAsync(&h, s->flag, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CK(cudaStreamSynchronize(s->st));
+  }
   if (h) { s->err = msg; return HG_ERR_NAN; }
   return 0;
 }
@@ -608,12 +684,14 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
   for (int d = 0; d < s->dim; ++d) std::swap(s->u[L_IP][d], s->u[L_IC][d]);
   // from here on: *_IP hold the state the iteration starts from
 
+  XCH(s, 1, s->u[L_IP][0], s->u[L_IP][1], s->u[L_IP][2], s->p[L_IP]);
   tpush(s, "fluid.0.pressure-gradient");
   DIMSEL(s, k_pre, gb, 256, s->geo, cp3(s->force), s->p[L_IP], p3(s->fcr), p3(s->gp));
   tpop(s);
   tpush(s, "fluid.1a.explicit-viscosity");
   { P9 G; for (int q = 0; q < 9; ++q) G.p[q] = s->G[q];
     DIMSEL(s, k_velgrad, gb, 256, s->geo, cp3(s->u[L_IP]), G);
+    if (s->world > 1) if (int rc = slab_exchange(s, s->G, s->dim * s->dim, 1)) return rc;
     P9c Gc; for (int q = 0; q < 9; ++q) Gc.p[q] = s->G[q];
     const int use_stf = (c.num_phases >= 2 && c.sigma != 0.) ? 1 : 0;
     DIMSEL(s, k_source, gb, 256, s->geo, Gc, s->mu, cp3(s->gp), cp3(s->fcr), cp3(s->stforce), use_stf, p3(s->fs)); }
@@ -646,6 +724,7 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
     else { k_apply_corr<2, 2><<<gb, 256, 0, s->st>>>(s->geo, cp3(s->u[L_IP]), cp3(s->X), p3(s->u[L_IC])); }
     ++s->launches; }
   tpop(s);
+  XCH(s, 1, s->u[L_IC][0], s->u[L_IC][1], s->u[L_IC][2], s->gp[0], s->gp[1], s->gp[2], s->fcr[0], s->fcr[1], s->fcr[2], s->dc);
   tpush(s, "fluid.3.momentum-interpolation");
   { FstarArgs a;
     for (int d = 0; d < 3; ++d) { a.us[d] = s->u[L_IC][d]; a.gp[d] = s->gp[d]; a.fcr[d] = s->fcr[d]; a.force[d] = s->force[d]; a.meshvel[d] = c.meshvel[d]; }
@@ -657,6 +736,7 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
     DIMSEL(s, k_prhs, gb, 256, s->geo, s->Fs, s->dc, 0, s->An[0], s->An[1], s->An[2], s->An[3], s->gs_tiled ? s->An[4] : nullptr);
     double* outs[5] = {s->RP, s->D, s->CYs, s->CZs, s->DGs};
     shear_arrays(s, s->An, outs, s->gs_tiled ? 5 : 4);
+    if (s->geo.zlo > 0) { k_cz_halo<3><<<nblk(s->nxy), 256, 0, s->st>>>(s->geo, s->dc, s->CZs); ++s->launches; }
   } else {
     DIMSEL(s, k_prhs, gb, 256, s->geo, s->Fs, s->dc, 1, s->RP, s->D, s->CYs, s->CZs, nullptr);
   }
@@ -664,6 +744,7 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
   tpush(s, "fluid.6.pressure-solve");
   if (int rc = solve_pressure(s)) return rc;
   tpop(s);
+  XCH(s, 1, s->pc);
   tpush(s, "fluid.7.correction");
   { CorrArgs a; a.pc = s->pc; a.dc = s->dc; a.Fs = s->Fs; a.F = s->F[L_IC];
     for (int d = 0; d < 3; ++d) a.u[d] = s->u[L_IC][d];
@@ -686,8 +767,7 @@ extern "C" int hg_fluid_convergence_indicator(hg_handle s, double* out) {
   if (s->iter_count == 0) { *out = 1.; return 0; }
   if (s->last_resid < 0.) {
     const int idx = s->iter_count - 1 < 4095 ? s->iter_count - 1 : 4095;
-    CK(cudaMemcpyAsync(s->hscal, s->resid + idx, sizeof(double), cudaMemcpyDeviceToHost, s->st));
-    CK(cudaStreamSynchronize(s->st));
+    if (int rc = slab_reduce(s, s->resid + idx, 1, 0, s->hscal)) return rc;
     s->last_resid = s->hscal[0];
   }
   *out = s->last_resid;
@@ -723,8 +803,7 @@ extern "C" int hg_fluid_auto_time_step(hg_handle s, double* out) {
   double init = 1e10;
   CK(cudaMemcpyAsync(s->scal + 1, &init, sizeof(double), cudaMemcpyHostToDevice, s->st));
   DIMSEL(s, k_auto_dt, nblk(s->nc), 256, s->geo, s->F[L_TC], s->scal + 1);
-  CK(cudaMemcpyAsync(s->hscal + 1, s->scal + 1, sizeof(double), cudaMemcpyDeviceToHost, s->st));
-  CK(cudaStreamSynchronize(s->st));
+  if (int rc = slab_reduce(s, s->scal + 1, 1, 1, s->hscal + 1)) return rc;
   *out = s->hscal[1];
   return 0;
 }
@@ -749,6 +828,7 @@ extern "C" int hg_advection_step(hg_handle s) {   // advection.hpp:417-545
     double* out = nullptr;
     for (int stage = 0; stage < num_stages; ++stage) {
       out = bufs[stage % 2];
+      XCH(s, 2, const_cast<double*>(in));
       DIMSEL(s, k_advect, nblk(s->nc), 256, s->geo, in, s->pd_init[ph], s->F[L_TC], s->dt_adv, num_stages, stage, out);
       in = out;
     }
@@ -876,6 +956,55 @@ static int fail_create(hg_state* s, int code, const std::string& msg) {
   return code;
 }
 
+// Initial fields, first UpdateFluidProperties + CalcStat (hydro2d.hpp:928-972).  On several GPUs this needs the
+// neighbouring slabs (smoothing, face fluxes), so it runs when the ranks have been linked.
+static int init_fields(hg_state* s) {
+  const hg_config& cfg = s->cfg;
+  Geo& g = s->geo;
+  const int dim = s->dim;
+  const long long nc = s->nc, nf = s->nf;
+  // initial fields
+  {
+    InitArgs a; memset(&a, 0, sizeof a);
+    for (int d = 0; d < 3; ++d) {
+      a.v0[d] = cfg.initial_velocity[d]; a.sin_n[d] = cfg.initial_sin_n[d];
+      a.A1[d] = cfg.A1[d]; a.B1[d] = cfg.B1[d]; a.A2[d] = cfg.A2[d]; a.B2[d] = cfg.B2[d]; a.IC[d] = cfg.IC[d]; a.IC2[d] = cfg.IC2[d];
+      a.u[d] = d < dim ? s->u[L_TC][d] : s->w1;
+    }
+    a.pois = cfg.initial_pois; a.sin_on = cfg.initial_sin_enable; a.sin_lambda = cfg.initial_sin_lambda; a.sin_phase = cfg.initial_sin_phase;
+    a.IR = cfg.IR; a.IR2 = cfg.IR2; a.np = cfg.num_phases;
+    for (int p = 0; p < 3; ++p) { a.density[p] = cfg.density[p]; a.ivf[p] = cfg.initial_volume_fraction[p]; a.pd[p] = p < cfg.num_phases ? s->pd[p][L_TC] : s->w1; }
+    DIMSEL(s, k_init_fields, nblk(nc), 256, g, a);
+    for (int ph = 1; ph < cfg.num_phases; ++ph) {
+      if (cfg.initial_volume_fraction_smooth_times > 0) {
+        if (int rc = smooth_field(s, s->pd[ph][L_TC], cfg.initial_volume_fraction_smooth_times, s->w1)) return rc;
+        cudaMemcpyAsync(s->pd[ph][L_TC], s->w1, nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st);
+      }
+    }
+    LAUNCH(s, k_pd0, nblk(nc), 256, cfg.num_phases, cfg.density[0], cfg.density[1], cfg.density[2],
+           cfg.num_phases > 1 ? s->pd[1][L_TC] : s->zero, cfg.num_phases > 2 ? s->pd[2][L_TC] : s->zero, s->pd[0][L_TC], nc);
+    for (int ph = 0; ph < cfg.num_phases; ++ph) {
+      cudaMemcpyAsync(s->pd_init[ph], s->pd[ph][L_TC], nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st);
+      cudaMemcpyAsync(s->pd[ph][L_TP], s->pd[ph][L_TC], nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st);
+    }
+    for (int d = 0; d < dim; ++d) cudaMemcpyAsync(s->u[L_TP][d], s->u[L_TC][d], nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st);
+    CP3 uu; for (int d = 0; d < 3; ++d) uu.p[d] = d < dim ? s->u[L_TC][d] : s->zero;
+    XCH(s, 1, s->u[L_TC][0], s->u[L_TC][1], s->u[L_TC][2]);
+    DIMSEL(s, k_init_flux, nblk(nc), 256, g, uu, cfg.meshvel[0], cfg.meshvel[1], cfg.meshvel[2], s->F[L_TC]);
+    cudaMemcpyAsync(s->F[L_TP], s->F[L_TC], nf * sizeof(double), cudaMemcpyDeviceToDevice, s->st);
+    if (cfg.heat_enable) {
+      LAUNCH(s, k_fill, nblk(nc), 256, s->T[L_TC], cfg.temperature_initial, nc);
+      LAUNCH(s, k_fill, nblk(nc), 256, s->T[L_TP], cfg.temperature_initial, nc);
+    }
+  }
+  if (int rc = hg_update_properties(s)) return rc;
+  if (int rc = hg_calc_stat(s, nullptr)) return rc;
+  CK(cudaStreamSynchronize(s->st));
+  CK(cudaGetLastError());
+  s->initialised = true;
+  return 0;
+}
+
 extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
   if (!cfg || !out) { g_create_err = "null argument"; return HG_ERR_INVALID; }
   *out = nullptr;
@@ -893,6 +1022,9 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     return fail_create(nullptr, HG_ERR_INVALID, "z-slab decomposition needs dim 3 and at least 2 planes per rank");
   if (cfg->world_size > 1 && (cfg->linear_solver_pressure == HG_LS_LU_RELAXED || cfg->linear_solver_pressure == HG_LS_JACOBI))
     return fail_create(nullptr, HG_ERR_INVALID, "multi-GPU slabs support gauss_seidel for the pressure system");
+  if (cfg->world_size > 1 && (cfg->heat_enable || (cfg->num_phases >= 2 && cfg->sigma != 0.)))
+    return fail_create(nullptr, HG_ERR_INVALID, "multi-GPU slabs: heat_enable / surface tension are not decomposed yet");
+  if (cfg->world_size > SLAB_MAX_WORLD) return fail_create(nullptr, HG_ERR_INVALID, "world_size too large");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
     return fail_create(nullptr, HG_ERR_NO_DEVICE, "no CUDA device: the GPU path has no CPU fallback");
@@ -1019,6 +1151,9 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
   if (occ_gs < 1 || occ_lu < 1) return fail_create(s, HG_ERR_CUDA, "solver kernel does not fit on an SM");
   s->grid_solver = prop.multiProcessorCount * std::min(occ_gs, 1);
   s->grid_lu = prop.multiProcessorCount * std::min(occ_lu, 1);
+  if (cfg->solver_ctas > 0) {   // several ranks sharing one device (tests): their persistent kernels must be co-resident
+    s->grid_solver = std::min(s->grid_solver, cfg->solver_ctas); s->grid_lu = std::min(s->grid_lu, cfg->solver_ctas);
+  }
 
   // hyperplane tile table for the ordered sweeps (hg_solvers.cuh)
   {
@@ -1074,51 +1209,116 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     if (kg >= s->k0 - g.zlo && kg < s->k1 + g.zhi) g.pfix = best - (long long)s->k0 * g.sz;   // local index, may be in a halo plane
   }
   s->dt = cfg->dt; s->dt_adv = cfg->dt * cfg->advection_dt_factor;
-
-  // initial fields
-  {
-    InitArgs a; memset(&a, 0, sizeof a);
-    for (int d = 0; d < 3; ++d) {
-      a.v0[d] = cfg->initial_velocity[d]; a.sin_n[d] = cfg->initial_sin_n[d];
-      a.A1[d] = cfg->A1[d]; a.B1[d] = cfg->B1[d]; a.A2[d] = cfg->A2[d]; a.B2[d] = cfg->B2[d]; a.IC[d] = cfg->IC[d]; a.IC2[d] = cfg->IC2[d];
-      a.u[d] = d < dim ? s->u[L_TC][d] : s->w1;
-    }
-    a.pois = cfg->initial_pois; a.sin_on = cfg->initial_sin_enable; a.sin_lambda = cfg->initial_sin_lambda; a.sin_phase = cfg->initial_sin_phase;
-    a.IR = cfg->IR; a.IR2 = cfg->IR2; a.np = cfg->num_phases;
-    for (int p = 0; p < 3; ++p) { a.density[p] = cfg->density[p]; a.ivf[p] = cfg->initial_volume_fraction[p]; a.pd[p] = p < cfg->num_phases ? s->pd[p][L_TC] : s->w1; }
-    DIMSEL(s, k_init_fields, nblk(nc), 256, g, a);
-    for (int ph = 1; ph < cfg->num_phases; ++ph) {
-      if (cfg->initial_volume_fraction_smooth_times > 0) {
-        if (smooth_field(s, s->pd[ph][L_TC], cfg->initial_volume_fraction_smooth_times, s->w1)) return fail_create(s, HG_ERR_CUDA, s->err);
-        cudaMemcpyAsync(s->pd[ph][L_TC], s->w1, nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st);
-      }
-    }
-    LAUNCH(s, k_pd0, nblk(nc), 256, cfg->num_phases, cfg->density[0], cfg->density[1], cfg->density[2],
-           cfg->num_phases > 1 ? s->pd[1][L_TC] : s->zero, cfg->num_phases > 2 ? s->pd[2][L_TC] : s->zero, s->pd[0][L_TC], nc);
-    for (int ph = 0; ph < cfg->num_phases; ++ph) {
-      cudaMemcpyAsync(s->pd_init[ph], s->pd[ph][L_TC], nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st);
-      cudaMemcpyAsync(s->pd[ph][L_TP], s->pd[ph][L_TC], nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st);
-    }
-    for (int d = 0; d < dim; ++d) cudaMemcpyAsync(s->u[L_TP][d], s->u[L_TC][d], nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st);
-    CP3 uu; for (int d = 0; d < 3; ++d) uu.p[d] = d < dim ? s->u[L_TC][d] : s->zero;
-    DIMSEL(s, k_init_flux, nblk(nc), 256, g, uu, cfg->meshvel[0], cfg->meshvel[1], cfg->meshvel[2], s->F[L_TC]);
-    cudaMemcpyAsync(s->F[L_TP], s->F[L_TC], nf * sizeof(double), cudaMemcpyDeviceToDevice, s->st);
-    if (cfg->heat_enable) {
-      LAUNCH(s, k_fill, nblk(nc), 256, s->T[L_TC], cfg->temperature_initial, nc);
-      LAUNCH(s, k_fill, nblk(nc), 256, s->T[L_TP], cfg->temperature_initial, nc);
-    }
+  if (s->world > 1) {
+    Slab& sl = s->slab;
+    sl.world = s->world; sl.rank = s->rank; sl.has_lo = s->rank > 0; sl.has_hi = s->rank + 1 < s->world;
+    sl.np_glob = s->n[0] + s->n[1] + s->nzg - 2;
+    if (sl.has_lo) { const int base = s->nzg / s->world, rem = s->nzg % s->world; sl.nz_lo = base + (s->rank - 1 < rem ? 1 : 0); }
   }
-  if (hg_update_properties(s) || hg_calc_stat(s, nullptr)) return fail_create(s, HG_ERR_CUDA, s->err);
-  if (cudaStreamSynchronize(s->st) != cudaSuccess || cudaGetLastError() != cudaSuccess)
-    return fail_create(s, HG_ERR_CUDA, std::string("initialisation failed: ") + cudaGetErrorString(cudaGetLastError()));
+
+  if (s->world > 1) {
+    // load the kernels that only decomposed runs launch now: a first launch (lazy module loading) synchronises the
+    // context, which dead-locks ranks that share a device while one waits for the other inside a kernel
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, k_slab_pack); cudaFuncGetAttributes(&fa, k_slab_signal); cudaFuncGetAttributes(&fa, k_slab_wait);
+    cudaFuncGetAttributes(&fa, k_slab_unpack); cudaFuncGetAttributes(&fa, k_mail_post); cudaFuncGetAttributes(&fa, k_mail_wait);
+    cudaFuncGetAttributes(&fa, k_cz_halo<3>); cudaFuncGetAttributes(&fa, k_flag_to_double);
+    cudaGetLastError();
+  }
+  // no allocation after this point on the stepping path: cudaMalloc synchronises the device, which dead-locks
+  // ranks that share a device while one of them waits for the other inside a kernel
+  if (ensure_sweep_capacity(s, std::max(cfg->lu_relaxed_num_iters_limit + 1, 64))) return fail_create(s, HG_ERR_CUDA, s->err);
+  if (s->world == 1) {
+    if (init_fields(s)) return fail_create(s, HG_ERR_CUDA, s->err);
+  } else if (cudaStreamSynchronize(s->st) != cudaSuccess) {
+    return fail_create(s, HG_ERR_CUDA, "initialisation failed");
+  }
   *out = s;
   return 0;
+}
+
+// ------------------------------------------------------------------ linking the ranks of a slab decomposition
+// One process per GPU: every rank exports CUDA IPC handles of the few buffers its neighbours touch
+// (hg_ipc_export), the host side all-gathers the records (torch.distributed / MPI / files: plumbing), every rank
+// imports them (hg_ipc_import).  Ranks living in one process (tests; several ranks on one device) are linked by
+// pointer (hg_link_local).  Linking is collective: it ends with the initial fields, which need the neighbours.
+struct hg_ipc_record { cudaIpcMemHandle_t xbuf, mail, PP, X[3]; };
+extern "C" size_t hg_ipc_record_size(void) { return sizeof(hg_ipc_record); }
+
+extern "C" int hg_ipc_export(hg_handle s, void* buf, size_t cap) {
+  if (!s || !buf || cap < sizeof(hg_ipc_record)) return HG_ERR_INVALID;
+  if (s->world <= 1) { s->err = "hg_ipc_export: single-GPU handle"; return HG_ERR_INVALID; }
+  cudaSetDevice(s->dev);
+  hg_ipc_record r; memset(&r, 0, sizeof r);
+  CK(cudaIpcGetMemHandle(&r.xbuf, s->slab.xbuf));
+  CK(cudaIpcGetMemHandle(&r.mail, s->slab.mail));
+  CK(cudaIpcGetMemHandle(&r.PP, s->PP));
+  for (int n = 0; n < 3; ++n) CK(cudaIpcGetMemHandle(&r.X[n], s->X[n]));
+  memcpy(buf, &r, sizeof r);
+  return 0;
+}
+
+static int finish_link(hg_state* s) {
+  s->slab.mail_peer[s->rank] = s->slab.mail;
+  s->slab.linked = true;
+  return init_fields(s);
+}
+
+extern "C" int hg_ipc_import(hg_handle s, const void* all_records) {
+  if (!s || !all_records) return HG_ERR_INVALID;
+  if (s->world <= 1) { s->err = "hg_ipc_import: single-GPU handle"; return HG_ERR_INVALID; }
+  cudaSetDevice(s->dev);
+  const hg_ipc_record* rec = (const hg_ipc_record*)all_records;
+  auto open = [&](const cudaIpcMemHandle_t& h, double** out) -> int {
+    void* q = nullptr;
+    CK(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+    s->ipc_opened.push_back(q);
+    *out = (double*)q;
+    return 0;
+  };
+  Slab& sl = s->slab;
+  for (int r = 0; r < s->world; ++r) if (r != s->rank) if (int rc = open(rec[r].mail, &sl.mail_peer[r])) return rc;
+  if (sl.has_lo) {
+    double* q = nullptr;
+    if (int rc = open(rec[s->rank - 1].xbuf, &q)) return rc;
+    sl.xbuf_lo = q;
+    if (int rc = open(rec[s->rank - 1].PP, &sl.PP_lo)) return rc;
+    for (int n = 0; n < s->dim; ++n) if (int rc = open(rec[s->rank - 1].X[n], &sl.X_lo[n])) return rc;
+  }
+  if (sl.has_hi) {
+    double* q = nullptr;
+    if (int rc = open(rec[s->rank + 1].xbuf, &q)) return rc;
+    sl.xbuf_hi = q;
+    if (int rc = open(rec[s->rank + 1].PP, &sl.PP_hi)) return rc;
+    for (int n = 0; n < s->dim; ++n) if (int rc = open(rec[s->rank + 1].X[n], &sl.X_hi[n])) return rc;
+  }
+  return finish_link(s);
+}
+
+extern "C" int hg_link_local(hg_handle s, const hg_handle* all) {
+  if (!s || !all) return HG_ERR_INVALID;
+  if (s->world <= 1) { s->err = "hg_link_local: single-GPU handle"; return HG_ERR_INVALID; }
+  cudaSetDevice(s->dev);
+  Slab& sl = s->slab;
+  for (int r = 0; r < s->world; ++r) {
+    if (!all[r] || all[r]->world != s->world || all[r]->rank != r) { s->err = "hg_link_local: handles must be given in rank order"; return HG_ERR_INVALID; }
+    if (all[r]->dev != s->dev) {
+      cudaError_t e = cudaDeviceEnablePeerAccess(all[r]->dev, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { s->err = "peer access between the devices is not available"; return HG_ERR_CUDA; }
+      cudaGetLastError();
+    }
+    sl.mail_peer[r] = all[r]->slab.mail;
+  }
+  if (sl.has_lo) { hg_state* o = all[s->rank - 1]; sl.xbuf_lo = o->slab.xbuf; sl.PP_lo = o->PP; for (int n = 0; n < 3; ++n) sl.X_lo[n] = o->X[n]; }
+  if (sl.has_hi) { hg_state* o = all[s->rank + 1]; sl.xbuf_hi = o->slab.xbuf; sl.PP_hi = o->PP; for (int n = 0; n < 3; ++n) sl.X_hi[n] = o->X[n]; }
+  return finish_link(s);
 }
 
 extern "C" int hg_destroy(hg_handle s) {
   if (!s) return 0;
   cudaSetDevice(s->dev);
   cudaStreamSynchronize(s->st);
+  for (void* p : s->ipc_opened) cudaIpcCloseMemHandle(p);
   for (void* p : s->allocs) cudaFree(p);
   if (s->hscal) cudaFreeHost(s->hscal);
   if (s->hdiffs) cudaFreeHost(s->hdiffs);

@@ -16,7 +16,8 @@ The reference has no decomposition (its MPI is a stub, source/main.cpp:26-28), s
   (tests/test_parallel_cpu.py, gloo, world_size 2 and 3).  On the device the same messages are peer-memory
   stores over NVLink followed by a system-scope flag (one handshake per step), see DESIGN.md.
 
-This round the device path runs one slab per handle only for world_size 1; bench.py --gpus N runs replicas.
+The device path: hydro_b200/csrc/hg_slab.cuh + the slab-aware kernels; `run_local_ranks` drives several ranks from one
+process (tests), bench.py one rank per process under torchrun.
 """
 from dataclasses import dataclass
 
@@ -171,3 +172,73 @@ def _exchange(dist, slab, x, send_up, send_dn):
         plane = 0 if peer == slab.lower else slab.nzl + 1   # lower rank's top plane -> my bottom halo, and v.v.
         for j, i, v in vals:
             x[plane, int(j), int(i)] = v
+
+
+# ---------------------------------------------------------------- driving the device path
+def join_cells(parts):
+    """Cell field of the whole mesh from the ranks' slabs (a slab is a contiguous range of the raw order)."""
+    return np.concatenate(parts)
+
+
+def join_faces(parts, nx, ny, nz, world):
+    """Face field (x-, y-, z-blocks, mesh.hpp:698-705) of the whole mesh from the ranks' local face arrays;
+    interface z-faces exist on both neighbours (identical values): the lower rank's copy is dropped."""
+    xs, ys, zs = [], [], []
+    for r, f in enumerate(parts):
+        k0, k1 = slab_range(nz, world, r)
+        nzl = k1 - k0
+        nxf, nyf = (nx + 1) * ny * nzl, nx * (ny + 1) * nzl
+        xs.append(f[:nxf])
+        ys.append(f[nxf:nxf + nyf])
+        z = f[nxf + nyf:].reshape(nzl + 1, ny * nx)
+        zs.append(z if r == world - 1 else z[:-1])
+    return np.concatenate(xs + ys + [z.reshape(-1) for z in zs])
+
+
+def run_local_ranks(params, world, nsteps, fields, devices=None, solver_ctas=0, timeout=120.0):
+    """Runs `world` slab ranks in this process, one thread per rank (the C calls release the GIL), and returns
+    (stats of the last step of rank 0, {field: whole-mesh array}).  devices: one per rank (default: all on 0,
+    which needs solver_ctas <= SMs / world so that the ranks' persistent kernels are co-resident)."""
+    import threading
+    from .capi import Hydro
+    from .config import FACE_FIELDS, F
+    devices = devices or [0] * world
+    hs, errs, out, stats = [None] * world, [], [None] * world, [None] * world
+    bar = threading.Barrier(world)
+
+    def work(r):
+        try:
+            hs[r] = Hydro(params, device=devices[r], world_size=world, rank=r, solver_ctas=solver_ctas)
+        except Exception as e:   # noqa: BLE001
+            errs.append((r, e))
+        try:
+            bar.wait(timeout)
+            if errs:
+                return
+            hs[r].link_local(hs)
+            st = None
+            for _ in range(nsteps):
+                st = hs[r].step()
+            stats[r] = st
+            out[r] = {n: hs[r].get(n) for n in fields}
+        except Exception as e:   # noqa: BLE001
+            errs.append((r, e))
+
+    th = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout)
+    if errs:
+        raise RuntimeError("rank %d: %s" % (errs[0][0], errs[0][1]))
+    if any(t.is_alive() for t in th):
+        raise RuntimeError("slab ranks did not finish")
+    p = params
+    nx, ny, nz = int(p["Nx"]), int(p["Ny"]), int(p["Nz"])
+    whole = {}
+    for n in fields:
+        parts = [out[r][n] for r in range(world)]
+        whole[n] = join_faces(parts, nx, ny, nz, world) if F[n] in FACE_FIELDS else join_cells(parts)
+    for h in hs:
+        h.close()
+    return stats[0], whole

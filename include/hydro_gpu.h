@@ -142,7 +142,8 @@ typedef struct hg_config {
   const void* nccl_unique_id;
   /* execution options */
   int pressure_sweeps_per_check;   /* 0 = default */
-  int reserved[7];
+  int solver_ctas;                 /* 0 = one CTA per SM; >0 limits the persistent solver grids (ranks sharing a device) */
+  int reserved[6];
 } hg_config;
 
 /* statistics of one hg_step, reference: P_int["s"], CalcStat (hydro2d.hpp:1432-1529) */
@@ -168,6 +169,18 @@ void hg_config_defaults(hg_config* cfg);
 int hg_create(const hg_config* cfg, hg_handle* out);
 int hg_destroy(hg_handle h);
 const char* hg_last_error(hg_handle h); /* h may be NULL: error of the last failed hg_create */
+
+/* Slab decomposition (world_size > 1), one handle per GPU.  hg_create allocates; the ranks are then linked
+ * -- collectively, every rank calls one of the two -- and the initial fields are computed:
+ *   separate processes: hg_ipc_export fills one record (hg_ipc_record_size() bytes) with CUDA IPC handles of the
+ *     buffers the neighbouring ranks touch; the caller all-gathers the records (any transport) and passes the
+ *     world_size records, in rank order, to hg_ipc_import;
+ *   one process: hg_link_local takes the world_size handles in rank order.
+ * The reference has nothing to replace here (its MPI is a stub, source/main.cpp:26-28). */
+size_t hg_ipc_record_size(void);
+int hg_ipc_export(hg_handle h, void* record, size_t cap);
+int hg_ipc_import(hg_handle h, const void* all_records);
+int hg_link_local(hg_handle h, const hg_handle* all_handles);
 
 size_t hg_num_cells(hg_handle h);  /* local cells of this rank's slab */
 size_t hg_num_faces(hg_handle h);

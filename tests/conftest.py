@@ -1,6 +1,10 @@
 import os
 import sys
 
+# Ranks of a slab decomposition that share one device (tests/test_multi_gpu.py) wait for each other inside kernels;
+# lazy module loading synchronises the context at a kernel's first launch and would dead-lock them.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,0 +1,62 @@
+"""z-slab decomposition on the device: the decomposed run must reproduce the single-GPU run bit for bit
+-- every kernel is cell-local given the halo planes, and the ordered solvers keep the global hyperplane schedule.
+
+The ranks live in this process (one thread each, hg_link_local).  With one visible GPU they share it (their
+persistent solver kernels are limited to a part of the SMs so that they are co-resident); with more GPUs every
+rank gets its own device and the halo planes / solver interface values travel over NVLink peer memory.
+"""
+import numpy as np
+import pytest
+
+import cases
+from hydro_b200 import parallel
+
+pytestmark = pytest.mark.gpu
+FIELDS = ["VELOCITY_X", "VELOCITY_Y", "VELOCITY_Z", "PRESSURE", "VOLUME_FLUX", "PARTIAL_DENSITY_0", "PARTIAL_DENSITY_1",
+          "DENSITY", "VISCOSITY", "FORCE_Y"]
+
+
+def single(p, nsteps):
+    from hydro_b200.capi import Hydro
+    h = Hydro(p)
+    st = [h.step() for _ in range(nsteps)][-1]
+    out = {n: h.get(n) for n in FIELDS}
+    h.close()
+    return st, out
+
+
+def devices_for(world):
+    import torch
+    n = torch.cuda.device_count()
+    return (list(range(world)), 0) if n >= world else ([0] * world, 148 // world - 2)
+
+
+@pytest.mark.parametrize("case,world", [("rt3d_16", 2), ("rt3d_20x12x17", 3), ("dam3d_32x10x12", 2), ("rt3d_tol", 2)])
+def test_slabs_equal_single_gpu(case, world, monkeypatch):
+    monkeypatch.setenv("HYDRO_GS_KERNEL", "hyperplane")   # same sweep kernel on both sides (bitwise equal anyway)
+    p = {"rt3d_16": cases.rt3d(16),
+         "rt3d_20x12x17": cases.rt3d(8, Nx=20, Ny=12, Nz=17, lu_relaxed_num_iters_limit=30),
+         "dam3d_32x10x12": cases.broken_dam_3d(32, 10, 12, lu_relaxed_num_iters_limit=40),
+         "rt3d_tol": cases.rt3d(12, fixed_work=False, lu_relaxed_num_iters_limit=200, lu_relaxed_tolerance=1e-6,
+                               num_iterations_limit=3, pressure_sweeps_per_check=32)}[case]
+    st1, f1 = single(p, 2)
+    devs, ctas = devices_for(world)
+    stn, fn = parallel.run_local_ranks(p, world, 2, FIELDS, devices=devs, solver_ctas=ctas)
+    assert stn.simple_iterations == st1.simple_iterations
+    assert stn.pressure_sweeps_total == st1.pressure_sweeps_total
+    assert stn.pressure_last_diff == st1.pressure_last_diff
+    assert stn.convergence_indicator == st1.convergence_indicator
+    for n in FIELDS:
+        assert np.array_equal(fn[n], f1[n]), n
+    for ph in range(2):
+        assert abs(stn.volume[ph] - st1.volume[ph]) <= 1e-12 * abs(st1.volume[ph])
+
+
+def test_single_gpu_matches_tiled_default():
+    """The default single-GPU configuration (tile sweeps) against the 2-slab run."""
+    p = cases.rt3d(24)
+    st1, f1 = single(p, 1)
+    devs, ctas = devices_for(2)
+    stn, fn = parallel.run_local_ranks(p, 2, 1, FIELDS, devices=devs, solver_ctas=ctas)
+    for n in FIELDS:
+        assert np.array_equal(fn[n], f1[n]), n
