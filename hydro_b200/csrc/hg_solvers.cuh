@@ -64,10 +64,11 @@ DV void grid_barrier(unsigned long long* bar, unsigned int nblocks, unsigned int
       do {
         asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(cur) : "l"(bar) : "memory");
       } while (cur < target);
+      // one system-scope fence (cumulative over the CTAs' release arrivals observed above), then plain flag stores
       __threadfence_system();
       const unsigned long long v = L.base + epoch + 1u;
-      if (L.has_lo) st_release_sys(L.lo_flags + SF_S_HI, v);
-      if (L.has_hi) st_release_sys(L.hi_flags + SF_S_LO, v);
+      if (L.has_lo) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(L.lo_flags + SF_S_HI), "l"(v) : "memory");
+      if (L.has_hi) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(L.hi_flags + SF_S_LO), "l"(v) : "memory");
       if (L.has_lo) slab_wait(L.my_flags + SF_S_LO, v, L.my_flags + SF_ERR);
       if (L.has_hi) slab_wait(L.my_flags + SF_S_HI, v, L.my_flags + SF_ERR);
       asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(L.go), "l"((unsigned long long)(epoch + 1u)) : "memory");
@@ -208,9 +209,11 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_gs_persistent(Geo g, GsAr
         const double corr = value - xold;
         const double xnew = xold + corr * a.omega;
         a.PP[cs] = xnew;
-        if (L.on && DIM > 2) {   // interface cells: the new value is also the neighbour slab's halo value
-          if (k == g.n[2] - 1 && L.has_hi) { a.PP_hi[((long long)(i + j) * g.n[1] + j) * nx + i] = xnew; __threadfence_system(); }
-          if (k == 0 && L.has_lo) { a.PP_lo[((long long)(i + j + L.nz_lo + 1) * g.n[1] + j) * nx + i] = xnew; __threadfence_system(); }
+        // interface cells: the new value is also the neighbour slab's halo value (peer store; made visible by the
+        // system-scope fence + flag of the step barrier, which is cumulative over the CTAs' release arrivals)
+        if (L.on && DIM > 2) {
+          if (k == g.n[2] - 1 && L.has_hi) { a.PP_hi[((long long)(i + j) * g.n[1] + j) * nx + i] = xnew; }
+          if (k == 0 && L.has_lo) { a.PP_lo[((long long)(i + j + L.nz_lo + 1) * g.n[1] + j) * nx + i] = xnew; }
         }
         ac = fabs(corr);
         if (!(ac == ac)) ac = 0.;
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_lu_persistent(Geo g, LuAr
         if (xm) sum += axm * __ldcg(&a.X[n][cs - PS - 1]);
         const double xv = (-a.R[n][cs] - sum) / diag;
         a.X[n][cs] = xv;
-        if (L.on && DIM > 2 && k == g.n[2] - 1 && L.has_hi) { a.X_hi[n][((long long)(i + j) * g.n[1] + j) * nx + i] = xv; __threadfence_system(); }
+        if (L.on && DIM > 2 && k == g.n[2] - 1 && L.has_hi) { a.X_hi[n][((long long)(i + j) * g.n[1] + j) * nx + i] = xv; }
       }
     }
     grid_barrier(a.tt.bar, gridDim.x, epoch, L);
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_lu_persistent(Geo g, LuAr
         if (xp) sum += axp * __ldcg(&a.X[n][cs + PS + 1]);
         const double xv = __ldcg(&a.X[n][cs]) - sum / diag;
         a.X[n][cs] = xv;
-        if (L.on && DIM > 2 && k == 0 && L.has_lo) { a.X_lo[n][((long long)(i + j + L.nz_lo + 1) * g.n[1] + j) * nx + i] = xv; __threadfence_system(); }
+        if (L.on && DIM > 2 && k == 0 && L.has_lo) { a.X_lo[n][((long long)(i + j + L.nz_lo + 1) * g.n[1] + j) * nx + i] = xv; }
       }
     }
     grid_barrier(a.tt.bar, gridDim.x, epoch, L);

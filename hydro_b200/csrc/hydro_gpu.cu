@@ -662,6 +662,8 @@ extern "C" int hg_fluid_start_step(hg_handle s) {   // fluid.hpp:793-812
   cudaSetDevice(s->dev);
   s->iter_count = 0;
   CK(cudaMemsetAsync(s->resid, 0, 4096 * sizeof(double), s->st));
+  // slabs: the caller may have set density / viscosity / force since the last hg_update_properties
+  XCH(s, 1, s->rho, s->mu, s->force[0], s->force[1], s->dim > 2 ? s->force[2] : nullptr);
   if (int rc = check_nan(s, s->p[L_TC], s->nc, "NaN initial pressure")) return rc;
   const double ge = s->cfg.guess_extrapolation;
   for (int d = 0; d < s->dim; ++d) {
