@@ -9,10 +9,11 @@
 //   mail   mailbox + flag words: every rank pushes its partial scalars (max-norms, CalcStat sums, NaN flags)
 //          into every rank's mailbox; the reduction is then done locally in rank order (deterministic and
 //          identical on all ranks, so the control flow -- iteration and sweep counts -- stays in lockstep);
-//   PP, X  the sheared solution arrays of the ordered sweeps: the thread that updates an interface cell also
-//          stores the new value into the neighbour's halo plane (the z- dependency of the upper slab in the same
-//          sweep, the z+ dependency of the lower slab in the next one), and the per-hyperplane grid barrier is
-//          extended by a system-scope flag handshake with both neighbours (hg_solvers.cuh).
+//   ll     interface planes of the ordered sweeps (Gauss-Seidel, lu): the thread that updates an interface cell
+//          stores {low word, tag, high word, tag} (16 bytes, each half written atomically) into the neighbour's
+//          plane; the thread that needs the value -- the z- dependency of the upper slab in the same sweep, the z+
+//          dependency of the lower slab in the next one -- polls until both tags carry the sweep it expects.  The
+//          data is its own flag: no fence, no handshake, one NVLink latency per hyperplane step (hg_solvers.cuh).
 // Staging and mailbox are double-buffered by sequence parity: a rank can never be two exchanges ahead of a
 // neighbour, because every exchange needs that neighbour's flag.
 #pragma once
@@ -32,9 +33,13 @@ struct Slab {
   const double* xbuf_lo = nullptr;
   const double* xbuf_hi = nullptr;
   double* mail_peer[SLAB_MAX_WORLD + 8] = {};
-  double *PP_lo = nullptr, *PP_hi = nullptr;
-  double *X_lo[3] = {}, *X_hi[3] = {};
-  unsigned long long xseq = 0, mseq = 0, hseq = 0;
+  // tagged interface planes: [0] Gauss-Seidel from below, [1] from above, [2+n] lu component n from below,
+  // [5+n] from above, [8],[9] checkpoint of [0],[1]; nxy entries each
+  uint4* ll = nullptr;          // mine (neighbours write [0], [2..4] / [1], [5..7])
+  uint4* ll_lower = nullptr;    // the lower neighbour's block (I write its planes "from above")
+  uint4* ll_upper = nullptr;    // the upper neighbour's block (I write its planes "from below")
+  unsigned solve_seq = 0, lu_seq = 0;
+  unsigned long long xseq = 0, mseq = 0;
   bool linked = false;
 };
 
@@ -131,15 +136,41 @@ __global__ void k_mail_wait(double* mymail, int world, unsigned long long v) {
   if (t < world) slab_wait(slab_flags(mymail, world) + SF_MAIL0 + t, v, slab_flags(mymail, world) + SF_ERR);
 }
 
+constexpr int SLAB_LL_PLANES = 10;
+// tagged 16-byte transport of one double (the scheme of NCCL's LL protocol): each 8-byte half is stored atomically
+// and carries the tag, so a reader that sees the expected tag in both halves has the whole value
+DV void ll_store(uint4* p, double v, unsigned tag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"((unsigned)b), "r"(tag), "r"((unsigned)(b >> 32)), "r"(tag) : "memory");
+}
+DV double ll_wait(const uint4* p, unsigned tag, unsigned long long* err) {
+  unsigned x, t0_, y, t1_;
+  long long t0 = 0;
+  for (unsigned spins = 0;; ++spins) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(t0_), "=r"(y), "=r"(t1_) : "l"(p) : "memory");
+    if (t0_ == tag && t1_ == tag) break;
+    if ((spins & 0x3ff) == 0x3ff) {   // bounded (about 4 s): see slab_wait
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 8000000000LL || *(volatile unsigned long long*)err) { *(volatile unsigned long long*)err = 1ull; break; }
+    }
+  }
+  return __longlong_as_double((long long)(((unsigned long long)y << 32) | x));
+}
+__global__ void k_ll_fill(uint4* p, long long n, unsigned tag) {   // value 0 with the given tag
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) p[t] = make_uint4(0u, tag, 0u, tag);
+}
 // what the ordered-sweep kernels need to talk to the neighbouring slabs
 struct SlabLink {
   int on;                         // 0 = single GPU
   int has_lo, has_hi, k0, np_glob, nz_lo;
-  unsigned long long* my_flags;   // my flag words (neighbours write SF_S_LO / SF_S_HI)
-  unsigned long long* lo_flags;   // lower neighbour's flag words (I write its SF_S_HI)
-  unsigned long long* hi_flags;   // upper neighbour's flag words (I write its SF_S_LO)
-  unsigned long long base;        // handshake counter value before this launch
-  unsigned long long* go;         // local release word for the extended barrier (zeroed by the host)
+  const uint4* from_lo;           // my plane written by the lower neighbour (values of its top cells)
+  const uint4* from_hi;           // my plane written by the upper neighbour (values of its bottom cells)
+  uint4* to_lo;                   // the lower neighbour's "from above" plane
+  uint4* to_hi;                   // the upper neighbour's "from below" plane
+  unsigned tag0;                  // tag of "before the first sweep of the solve"; sweep s of the solve carries tag0 + s + 1
+  unsigned long long* err;        // local error word (wait timed out)
 };
 
 // z+ face coefficients of the lower halo plane (k = -1): the sweep kernel reads them as the z- coupling of the

@@ -49,40 +49,6 @@ DV void grid_barrier(unsigned long long* bar, unsigned int nblocks, unsigned int
   ++epoch;
   __syncthreads();
 }
-// Barrier of a slab-decomposed sweep step: once all local CTAs have arrived, CTA 0 tells both neighbouring GPUs
-// "step base+epoch+1 done" (system-scope release store into their flag words, after the interface values
-// written into their halo planes), waits for the same from them, then releases the local CTAs.
-DV void grid_barrier(unsigned long long* bar, unsigned int nblocks, unsigned int& epoch, const SlabLink& L) {
-  if (!L.on) { grid_barrier(bar, nblocks, epoch); return; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned long long target = (unsigned long long)(epoch + 1u) * nblocks;
-    unsigned long long old, cur;
-    asm volatile("atom.add.release.gpu.global.u64 %0, [%1], 1;" : "=l"(old) : "l"(bar) : "memory");
-    (void)old;
-    if (blockIdx.x == 0) {
-      do {
-        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(cur) : "l"(bar) : "memory");
-      } while (cur < target);
-      // one system-scope fence (cumulative over the CTAs' release arrivals observed above), then plain flag stores
-      __threadfence_system();
-      const unsigned long long v = L.base + epoch + 1u;
-      if (L.has_lo) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(L.lo_flags + SF_S_HI), "l"(v) : "memory");
-      if (L.has_hi) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(L.hi_flags + SF_S_LO), "l"(v) : "memory");
-      if (L.has_lo) slab_wait(L.my_flags + SF_S_LO, v, L.my_flags + SF_ERR);
-      if (L.has_hi) slab_wait(L.my_flags + SF_S_HI, v, L.my_flags + SF_ERR);
-      asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(L.go), "l"((unsigned long long)(epoch + 1u)) : "memory");
-    } else {
-      do {
-        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(cur) : "l"(L.go) : "memory");
-      } while (cur < (unsigned long long)(epoch + 1u));
-    }
-    __threadfence();
-  }
-  ++epoch;
-  __syncthreads();
-}
-
 // Hyperplane tiles.  A tile is SOLVER_BY consecutive rows j x SOLVER_BX consecutive i of one plane
 // k' = i+j+k; only tiles that contain at least one cell are listed (built once per mesh on the host).
 struct TileTable {
@@ -134,7 +100,6 @@ struct GsArgs {
   double omega;
   TileTable tt;
   SlabLink link;       // neighbouring slabs (multi-GPU), link.on == 0 on a single GPU
-  double *PP_lo, *PP_hi;   // the neighbours' solution arrays (peer memory)
 };
 
 // Rows of the pressure-correction system (fluid.hpp:972-1014) are rebuilt on the fly from the three face
@@ -144,17 +109,15 @@ template <int DIM, bool EXCL>
 __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_gs_persistent(Geo g, GsArgs a) {
   __shared__ int sc[SOLVER_SC];
   const int S = a.s_end - a.s_begin;
-  // slab decomposition: all ranks walk the GLOBAL hyperplane schedule; this rank's plane of sweep s at global
-  // step Tg is Tg - 2 s - k0
+  // slab decomposition: every rank walks its own hyperplanes; the interface values arrive tagged with their sweep
+  // (ll_wait), which is all the coupling the lexicographic order needs
   const SlabLink L = a.link;
-  const int Tmax = ((L.on ? L.np_glob : g.np) - 1) + 2 * (S - 1);
-  const int koff = L.on ? L.k0 : 0;
+  const int Tmax = (g.np - 1) + 2 * (S - 1);
   const long long PS = (long long)g.n[1] * g.n[0];   // plane stride of the sheared layout
   const int nx = g.n[0];
   const int gslot = blockIdx.x * SOLVER_SLOTS + (threadIdx.x / SOLVER_TILE), nslots = gridDim.x * SOLVER_SLOTS;
   unsigned int epoch = 0;
-  for (int Tg = 0; Tg <= Tmax; ++Tg) {
-    const int T = Tg - koff;
+  for (int T = 0; T <= Tmax; ++T) {
     const StepTiles st = step_tiles(g, a.tt, T, S);
     fill_step_table(a.tt, st, sc);
     // contiguous id range per slot (neighbouring tiles share rows -> cache reuse); first plane by binary search
@@ -189,7 +152,12 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_gs_persistent(Geo g, GsAr
         const double czm = in_zm ? a.CZ[cs - PS] : 0.;
         const double pxm = in_xm ? __ldcg(&a.PP[cs - PS - 1]) : 0., pxp = in_xp ? __ldcg(&a.PP[cs + PS + 1]) : 0.;
         const double pym = in_ym ? __ldcg(&a.PP[cs - PS - nx]) : 0., pyp = in_yp ? __ldcg(&a.PP[cs + PS + nx]) : 0.;
-        const double pzm = in_zm ? __ldcg(&a.PP[cs - PS]) : 0., pzp = in_zp ? __ldcg(&a.PP[cs + PS]) : 0.;
+        // slab interfaces: the neighbour's value arrives tagged with its sweep; z- needs this sweep, z+ the previous one
+        const long long c2 = (long long)j * nx + i;
+        const unsigned tg = L.tag0 + (unsigned)(a.s_begin + s);
+        double pzm = 0., pzp = 0.;
+        if (in_zm) pzm = (k > 0 || !L.on) ? __ldcg(&a.PP[cs - PS]) : ll_wait(L.from_lo + c2, tg + 1u, L.err);
+        if (in_zp) pzp = (k + 1 < g.n[2] || !L.on) ? __ldcg(&a.PP[cs + PS]) : ll_wait(L.from_hi + c2, tg, L.err);
         double diag = 1., sum = 0.;
         if (!ident) {
           // diagonal: face order x-,x+,y-,y+,z-,z+ (fluid.hpp:979-984)
@@ -212,8 +180,8 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_gs_persistent(Geo g, GsAr
         // interface cells: the new value is also the neighbour slab's halo value (peer store; made visible by the
         // system-scope fence + flag of the step barrier, which is cumulative over the CTAs' release arrivals)
         if (L.on && DIM > 2) {
-          if (k == g.n[2] - 1 && L.has_hi) { a.PP_hi[((long long)(i + j) * g.n[1] + j) * nx + i] = xnew; }
-          if (k == 0 && L.has_lo) { a.PP_lo[((long long)(i + j + L.nz_lo + 1) * g.n[1] + j) * nx + i] = xnew; }
+          if (k == g.n[2] - 1 && L.has_hi) ll_store(L.to_hi + c2, xnew, tg + 1u);
+          if (k == 0 && L.has_lo) ll_store(L.to_lo + c2, xnew, tg + 1u);
         }
         ac = fabs(corr);
         if (!(ac == ac)) ac = 0.;
@@ -222,7 +190,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_gs_persistent(Geo g, GsAr
       ac = warp_max(ac);
       if ((threadIdx.x & 31) == 0 && ac > 0.) atomic_max_nonneg(&a.diff[a.s_begin + s], ac);
     }
-    grid_barrier(a.tt.bar, gridDim.x, epoch, L);
+    grid_barrier(a.tt.bar, gridDim.x, epoch);
   }
 }
 
@@ -233,8 +201,8 @@ struct LuArgs {
   double* X[3];         // sheared result
   int ncomp;
   TileTable tt;
-  SlabLink link;
-  double *X_lo[3], *X_hi[3];   // the neighbours' result arrays (peer memory)
+  SlabLink link;       // lu: planes [n] of from_lo/to_hi and from_hi/to_lo belong to component n (stride link_stride)
+  long long link_stride;
 };
 template <int DIM>
 __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_lu_persistent(Geo g, LuArgs a) {
@@ -242,12 +210,9 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_lu_persistent(Geo g, LuAr
   const int nx = g.n[0];
   const int gslot = blockIdx.x * SOLVER_SLOTS + (threadIdx.x / SOLVER_TILE), nslots = gridDim.x * SOLVER_SLOTS;
   const SlabLink L = a.link;
-  const int npg = L.on ? L.np_glob : g.np, koff = L.on ? L.k0 : 0;
   unsigned int epoch = 0;
-  // forward step (linear.hpp:537-548); global planes in ascending order, this rank's plane is P - k0
-  for (int P = 0; P < npg; ++P) {
-    const int kp = P - koff;
-    if (kp >= 0 && kp < g.np)
+  // forward step (linear.hpp:537-548), planes in ascending order
+  for (int kp = 0; kp < g.np; ++kp) {
     for (int e = a.tt.tileoff[kp] + gslot; e < a.tt.tileoff[kp + 1]; e += nslots) {
       int i, j, k;
       if (!tile_cell(g, a.tt, e, kp, i, j, k)) continue;
@@ -257,20 +222,18 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_lu_persistent(Geo g, LuAr
       const double diag = a.A[CD][cs];
       for (int n = 0; n < a.ncomp; ++n) {
         double sum = 0.;
-        if (zm) sum += azm * __ldcg(&a.X[n][cs - PS]);
+        if (zm) sum += azm * ((k > 0 || !L.on) ? __ldcg(&a.X[n][cs - PS]) : ll_wait(L.from_lo + n * a.link_stride + (long long)j * nx + i, L.tag0 + 1u, L.err));
         if (ym) sum += aym * __ldcg(&a.X[n][cs - PS - nx]);
         if (xm) sum += axm * __ldcg(&a.X[n][cs - PS - 1]);
         const double xv = (-a.R[n][cs] - sum) / diag;
         a.X[n][cs] = xv;
-        if (L.on && DIM > 2 && k == g.n[2] - 1 && L.has_hi) { a.X_hi[n][((long long)(i + j) * g.n[1] + j) * nx + i] = xv; }
+        if (L.on && DIM > 2 && k == g.n[2] - 1 && L.has_hi) ll_store(L.to_hi + n * a.link_stride + (long long)j * nx + i, xv, L.tag0 + 1u);
       }
     }
-    grid_barrier(a.tt.bar, gridDim.x, epoch, L);
+    grid_barrier(a.tt.bar, gridDim.x, epoch);
   }
   // backward step (linear.hpp:551-563)
-  for (int P = npg - 1; P >= 0; --P) {
-    const int kp = P - koff;
-    if (kp >= 0 && kp < g.np)
+  for (int kp = g.np - 1; kp >= 0; --kp) {
     for (int e = a.tt.tileoff[kp] + gslot; e < a.tt.tileoff[kp + 1]; e += nslots) {
       int i, j, k;
       if (!tile_cell(g, a.tt, e, kp, i, j, k)) continue;
@@ -280,15 +243,15 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_lu_persistent(Geo g, LuAr
       const double diag = a.A[CD][cs];
       for (int n = 0; n < a.ncomp; ++n) {
         double sum = 0.;
-        if (zp) sum += azp * __ldcg(&a.X[n][cs + PS]);
+        if (zp) sum += azp * ((k + 1 < g.n[2] || !L.on) ? __ldcg(&a.X[n][cs + PS]) : ll_wait(L.from_hi + n * a.link_stride + (long long)j * nx + i, L.tag0 + 2u, L.err));
         if (yp) sum += ayp * __ldcg(&a.X[n][cs + PS + nx]);
         if (xp) sum += axp * __ldcg(&a.X[n][cs + PS + 1]);
         const double xv = __ldcg(&a.X[n][cs]) - sum / diag;
         a.X[n][cs] = xv;
-        if (L.on && DIM > 2 && k == 0 && L.has_lo) { a.X_lo[n][((long long)(i + j + L.nz_lo + 1) * g.n[1] + j) * nx + i] = xv; }
+        if (L.on && DIM > 2 && k == 0 && L.has_lo) ll_store(L.to_lo + n * a.link_stride + (long long)j * nx + i, xv, L.tag0 + 2u);
       }
     }
-    grid_barrier(a.tt.bar, gridDim.x, epoch, L);
+    grid_barrier(a.tt.bar, gridDim.x, epoch);
   }
 }
 

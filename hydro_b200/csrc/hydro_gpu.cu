@@ -212,17 +212,19 @@ static int slab_sync(hg_state* s) {
 }
 #define XCH(s, planes, ...) \
   do { if ((s)->world > 1) { if (int rc_ = slab_exchange((s), {__VA_ARGS__}, (planes))) return rc_; } } while (0)
-static SlabLink slab_link(hg_state* s, unsigned long long nbarriers) {
+// what a linked solver kernel needs: which=0 Gauss-Seidel planes (tag0 = solve), which=1 lu planes (tag0 = lu solve)
+static SlabLink slab_link(hg_state* s, int which) {
   SlabLink L; memset(&L, 0, sizeof L);
   if (s->world <= 1) return L;
   Slab& sl = s->slab;
+  const long long nxy = s->nxy;
   L.on = 1; L.has_lo = sl.has_lo; L.has_hi = sl.has_hi; L.k0 = s->k0; L.np_glob = sl.np_glob; L.nz_lo = sl.nz_lo;
-  L.my_flags = slab_flags(sl.mail, s->world);
-  L.lo_flags = sl.has_lo ? slab_flags(sl.mail_peer[s->rank - 1], s->world) : nullptr;
-  L.hi_flags = sl.has_hi ? slab_flags(sl.mail_peer[s->rank + 1], s->world) : nullptr;
-  L.base = sl.hseq; sl.hseq += nbarriers;
-  TRACE("[r%d] solver link base %llu barriers %llu\n", s->rank, L.base, nbarriers);
-  L.go = s->tt.bar + 3;
+  L.from_lo = sl.ll + (which ? 2 : 0) * nxy;
+  L.from_hi = sl.ll + (which ? 5 : 1) * nxy;
+  L.to_lo = sl.has_lo ? sl.ll_lower + (which ? 5 : 1) * nxy : nullptr;
+  L.to_hi = sl.has_hi ? sl.ll_upper + (which ? 2 : 0) * nxy : nullptr;
+  L.tag0 = which ? sl.lu_seq * 4u : sl.solve_seq * 2048u;
+  L.err = slab_flags(sl.mail, s->world) + SF_ERR;
   return L;
 }
 
@@ -279,9 +281,16 @@ static int run_sor(hg_state* s, double* x, long long nx_, double tol, int limit,
   if (int rc = ensure_sweep_capacity(s, max_total)) return rc;
   CK(cudaMemsetAsync(x, 0, nx_ * sizeof(double), s->st));
   CK(cudaMemsetAsync(s->diffs, 0, max_total * sizeof(double), s->st));
-  // slabs: a neighbour's first sweep step stores into this rank's halo plane of x; it must not start before
-  // the reset above has been executed here
-  if (int rc = slab_sync(s)) return rc;
+  // slabs: the interface planes start as "value 0 before the first sweep"; a neighbour's first sweep step stores
+  // into them, so it must not start before the reset has been executed here
+  auto ll_reset = [&]() -> int {
+    if (s->world <= 1) return 0;
+    ++s->slab.solve_seq;
+    k_ll_fill<<<nblk(2 * s->nxy), 256, 0, s->st>>>(s->slab.ll, 2 * s->nxy, s->slab.solve_seq * 2048u);
+    ++s->launches;
+    return slab_sync(s);
+  };
+  if (int rc = ll_reset()) return rc;
   if (!(tol > 0.)) {
     // `diff > tol` only fails for diff == 0 (or NaN): run all limit+1 sweeps, inspect the history once
     for (int sb = 0; sb < max_total; sb += SOLVER_SC) {
@@ -295,7 +304,7 @@ static int run_sor(hg_state* s, double* x, long long nx_, double tol, int limit,
       const double dstop = s->hdiffs[stop];
       CK(cudaMemsetAsync(x, 0, nx_ * sizeof(double), s->st));
       CK(cudaMemsetAsync(s->diffs, 0, max_total * sizeof(double), s->st));
-      if (int rc = slab_sync(s)) return rc;
+      if (int rc = ll_reset()) return rc;
       for (int sb = 0; sb < stop + 1; sb += SOLVER_SC) if (int rc = launch(sb, std::min(sb + SOLVER_SC, stop + 1))) return rc;
       *out_iter = stop; *out_diff = dstop;
       return 0;
@@ -310,6 +319,7 @@ static int run_sor(hg_state* s, double* x, long long nx_, double tol, int limit,
   while (done < max_total) {
     int n = std::min(chunk, max_total - done);
     CK(cudaMemcpyAsync(s->PPsave, x, nx_ * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
+    if (s->world > 1) CK(cudaMemcpyAsync(s->slab.ll + 8 * s->nxy, s->slab.ll, 2 * s->nxy * sizeof(uint4), cudaMemcpyDeviceToDevice, s->st));
     if (int rc = launch(done, done + n)) return rc;
     if (int rc = slab_reduce(s, s->diffs + done, n, 0, s->hdiffs + done)) return rc;
     int stop = -1;
@@ -317,6 +327,7 @@ static int run_sor(hg_state* s, double* x, long long nx_, double tol, int limit,
     if (stop >= 0) {
       if (stop != done + n - 1) {
         CK(cudaMemcpyAsync(x, s->PPsave, nx_ * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
+        if (s->world > 1) CK(cudaMemcpyAsync(s->slab.ll, s->slab.ll + 8 * s->nxy, 2 * s->nxy * sizeof(uint4), cudaMemcpyDeviceToDevice, s->st));
         CK(cudaMemsetAsync(s->diffs + done, 0, n * sizeof(double), s->st));
         if (int rc = slab_sync(s)) return rc;
         if (int rc = launch(done, stop + 1)) return rc;
@@ -480,10 +491,7 @@ static int solve_pressure(hg_state* s) {
       if (s->gs_tiled) return gt_launch(s, sb, se, c.lu_relaxed_relaxation_factor);
       GsArgs a{}; a.CX = s->D; a.CY = s->CYs; a.CZ = s->CZs; a.RP = s->RP; a.PP = s->PP; a.diff = s->diffs; a.s_begin = sb; a.s_end = se;
       a.omega = c.lu_relaxed_relaxation_factor; a.tt = s->tt;
-      if (s->world > 1) {   // one neighbour handshake per global hyperplane step
-        a.link = slab_link(s, (unsigned long long)(s->slab.np_glob + 2 * (se - sb - 1)));
-        a.PP_lo = s->slab.PP_lo; a.PP_hi = s->slab.PP_hi;
-      }
+      a.link = slab_link(s, 0);
       if (s->dim == 3) return s->any_excl ? coop_launch(s, k_gs_persistent<3, true>, s->grid_solver, s->geo, a, 0)
                                           : coop_launch(s, k_gs_persistent<3, false>, s->grid_solver, s->geo, a, 0);
       return s->any_excl ? coop_launch(s, k_gs_persistent<2, true>, s->grid_solver, s->geo, a, 0)
@@ -536,10 +544,8 @@ static int solve_lu(hg_state* s, int ncomp) {
   for (int t = 0; t < 7; ++t) a.A[t] = s->A[t];
   for (int n = 0; n < 3; ++n) { a.R[n] = s->R[n]; a.X[n] = s->X[n]; }
   a.ncomp = ncomp; a.tt = s->tt;
-  if (s->world > 1) {
-    a.link = slab_link(s, 2ull * s->slab.np_glob);
-    for (int n = 0; n < 3; ++n) { a.X_lo[n] = s->slab.X_lo[n]; a.X_hi[n] = s->slab.X_hi[n]; }
-  }
+  if (s->world > 1) ++s->slab.lu_seq;
+  a.link = slab_link(s, 1); a.link_stride = s->nxy;
   if (s->dim == 3) return coop_launch(s, k_lu_persistent<3>, s->grid_lu, s->geo, a, 1);
   return coop_launch(s, k_lu_persistent<2>, s->grid_lu, s->geo, a, 1);
 }
@@ -1116,6 +1122,7 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     if (s->world > 1) {
       T.slab.xbuf = take(2LL * 2 * SLAB_MAX_ARRAYS * HG_HALO * s->nxy);
       T.slab.mail = take(2LL * s->world * SLAB_MAIL + 64);
+      T.slab.ll = (uint4*)take(2LL * SLAB_LL_PLANES * s->nxy);   // 16-byte entries
     }
     if (!okA) return fail_create(s, HG_ERR_CUDA, "allocation failed: " + s->err);
   }
@@ -1244,7 +1251,7 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
 // (hg_ipc_export), the host side all-gathers the records (torch.distributed / MPI / files: plumbing), every rank
 // imports them (hg_ipc_import).  Ranks living in one process (tests; several ranks on one device) are linked by
 // pointer (hg_link_local).  Linking is collective: it ends with the initial fields, which need the neighbours.
-struct hg_ipc_record { cudaIpcMemHandle_t xbuf, mail, PP, X[3]; };
+struct hg_ipc_record { cudaIpcMemHandle_t xbuf, mail, ll; };
 extern "C" size_t hg_ipc_record_size(void) { return sizeof(hg_ipc_record); }
 
 extern "C" int hg_ipc_export(hg_handle s, void* buf, size_t cap) {
@@ -1254,8 +1261,7 @@ extern "C" int hg_ipc_export(hg_handle s, void* buf, size_t cap) {
   hg_ipc_record r; memset(&r, 0, sizeof r);
   CK(cudaIpcGetMemHandle(&r.xbuf, s->slab.xbuf));
   CK(cudaIpcGetMemHandle(&r.mail, s->slab.mail));
-  CK(cudaIpcGetMemHandle(&r.PP, s->PP));
-  for (int n = 0; n < 3; ++n) CK(cudaIpcGetMemHandle(&r.X[n], s->X[n]));
+  CK(cudaIpcGetMemHandle(&r.ll, s->slab.ll));
   memcpy(buf, &r, sizeof r);
   return 0;
 }
@@ -1284,15 +1290,15 @@ extern "C" int hg_ipc_import(hg_handle s, const void* all_records) {
     double* q = nullptr;
     if (int rc = open(rec[s->rank - 1].xbuf, &q)) return rc;
     sl.xbuf_lo = q;
-    if (int rc = open(rec[s->rank - 1].PP, &sl.PP_lo)) return rc;
-    for (int n = 0; n < s->dim; ++n) if (int rc = open(rec[s->rank - 1].X[n], &sl.X_lo[n])) return rc;
+    if (int rc = open(rec[s->rank - 1].ll, &q)) return rc;
+    sl.ll_lower = (uint4*)q;
   }
   if (sl.has_hi) {
     double* q = nullptr;
     if (int rc = open(rec[s->rank + 1].xbuf, &q)) return rc;
     sl.xbuf_hi = q;
-    if (int rc = open(rec[s->rank + 1].PP, &sl.PP_hi)) return rc;
-    for (int n = 0; n < s->dim; ++n) if (int rc = open(rec[s->rank + 1].X[n], &sl.X_hi[n])) return rc;
+    if (int rc = open(rec[s->rank + 1].ll, &q)) return rc;
+    sl.ll_upper = (uint4*)q;
   }
   return finish_link(s);
 }
@@ -1311,8 +1317,8 @@ extern "C" int hg_link_local(hg_handle s, const hg_handle* all) {
     }
     sl.mail_peer[r] = all[r]->slab.mail;
   }
-  if (sl.has_lo) { hg_state* o = all[s->rank - 1]; sl.xbuf_lo = o->slab.xbuf; sl.PP_lo = o->PP; for (int n = 0; n < 3; ++n) sl.X_lo[n] = o->X[n]; }
-  if (sl.has_hi) { hg_state* o = all[s->rank + 1]; sl.xbuf_hi = o->slab.xbuf; sl.PP_hi = o->PP; for (int n = 0; n < 3; ++n) sl.X_hi[n] = o->X[n]; }
+  if (sl.has_lo) { hg_state* o = all[s->rank - 1]; sl.xbuf_lo = o->slab.xbuf; sl.ll_lower = o->slab.ll; }
+  if (sl.has_hi) { hg_state* o = all[s->rank + 1]; sl.xbuf_hi = o->slab.xbuf; sl.ll_upper = o->slab.ll; }
   return finish_link(s);
 }
 
