@@ -105,7 +105,7 @@ struct GsArgs {
 // Rows of the pressure-correction system (fluid.hpp:972-1014) are rebuilt on the fly from the three face
 // coefficient fields: diagonal = ordered sum of the six face coefficients (absent faces store 0, and
 // x + 0 == x, so the reference's "merge only existing terms" gives the same bits), off-diagonals = -c_f.
-template <int DIM, bool EXCL>
+template <int DIM, bool EXCL, bool LINK = false>
 __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_gs_persistent(Geo g, GsArgs a) {
   __shared__ int sc[SOLVER_SC];
   const int S = a.s_end - a.s_begin;
@@ -156,8 +156,8 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_gs_persistent(Geo g, GsAr
         const long long c2 = (long long)j * nx + i;
         const unsigned tg = L.tag0 + (unsigned)(a.s_begin + s);
         double pzm = 0., pzp = 0.;
-        if (in_zm) pzm = (k > 0 || !L.on) ? __ldcg(&a.PP[cs - PS]) : ll_wait(L.from_lo + c2, tg + 1u, L.err);
-        if (in_zp) pzp = (k + 1 < g.n[2] || !L.on) ? __ldcg(&a.PP[cs + PS]) : ll_wait(L.from_hi + c2, tg, L.err);
+        if (in_zm) pzm = (k > 0 || !LINK) ? __ldcg(&a.PP[cs - PS]) : ll_wait(L.from_lo + c2, tg + 1u, L.err);
+        if (in_zp) pzp = (k + 1 < g.n[2] || !LINK) ? __ldcg(&a.PP[cs + PS]) : ll_wait(L.from_hi + c2, tg, L.err);
         double diag = 1., sum = 0.;
         if (!ident) {
           // diagonal: face order x-,x+,y-,y+,z-,z+ (fluid.hpp:979-984)
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_gs_persistent(Geo g, GsAr
         a.PP[cs] = xnew;
         // interface cells: the new value is also the neighbour slab's halo value (peer store; made visible by the
         // system-scope fence + flag of the step barrier, which is cumulative over the CTAs' release arrivals)
-        if (L.on && DIM > 2) {
+        if (LINK && DIM > 2) {
           if (k == g.n[2] - 1 && L.has_hi) ll_store(L.to_hi + c2, xnew, tg + 1u);
           if (k == 0 && L.has_lo) ll_store(L.to_lo + c2, xnew, tg + 1u);
         }
@@ -204,7 +204,7 @@ struct LuArgs {
   SlabLink link;       // lu: planes [n] of from_lo/to_hi and from_hi/to_lo belong to component n (stride link_stride)
   long long link_stride;
 };
-template <int DIM>
+template <int DIM, bool LINK = false>
 __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_lu_persistent(Geo g, LuArgs a) {
   const long long PS = (long long)g.n[1] * g.n[0];
   const int nx = g.n[0];
@@ -222,12 +222,12 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_lu_persistent(Geo g, LuAr
       const double diag = a.A[CD][cs];
       for (int n = 0; n < a.ncomp; ++n) {
         double sum = 0.;
-        if (zm) sum += azm * ((k > 0 || !L.on) ? __ldcg(&a.X[n][cs - PS]) : ll_wait(L.from_lo + n * a.link_stride + (long long)j * nx + i, L.tag0 + 1u, L.err));
+        if (zm) sum += azm * ((k > 0 || !LINK) ? __ldcg(&a.X[n][cs - PS]) : ll_wait(L.from_lo + n * a.link_stride + (long long)j * nx + i, L.tag0 + 1u, L.err));
         if (ym) sum += aym * __ldcg(&a.X[n][cs - PS - nx]);
         if (xm) sum += axm * __ldcg(&a.X[n][cs - PS - 1]);
         const double xv = (-a.R[n][cs] - sum) / diag;
         a.X[n][cs] = xv;
-        if (L.on && DIM > 2 && k == g.n[2] - 1 && L.has_hi) ll_store(L.to_hi + n * a.link_stride + (long long)j * nx + i, xv, L.tag0 + 1u);
+        if (LINK && DIM > 2 && k == g.n[2] - 1 && L.has_hi) ll_store(L.to_hi + n * a.link_stride + (long long)j * nx + i, xv, L.tag0 + 1u);
       }
     }
     grid_barrier(a.tt.bar, gridDim.x, epoch);
@@ -243,12 +243,12 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 1) k_lu_persistent(Geo g, LuAr
       const double diag = a.A[CD][cs];
       for (int n = 0; n < a.ncomp; ++n) {
         double sum = 0.;
-        if (zp) sum += azp * ((k + 1 < g.n[2] || !L.on) ? __ldcg(&a.X[n][cs + PS]) : ll_wait(L.from_hi + n * a.link_stride + (long long)j * nx + i, L.tag0 + 2u, L.err));
+        if (zp) sum += azp * ((k + 1 < g.n[2] || !LINK) ? __ldcg(&a.X[n][cs + PS]) : ll_wait(L.from_hi + n * a.link_stride + (long long)j * nx + i, L.tag0 + 2u, L.err));
         if (yp) sum += ayp * __ldcg(&a.X[n][cs + PS + nx]);
         if (xp) sum += axp * __ldcg(&a.X[n][cs + PS + 1]);
         const double xv = __ldcg(&a.X[n][cs]) - sum / diag;
         a.X[n][cs] = xv;
-        if (L.on && DIM > 2 && k == 0 && L.has_lo) ll_store(L.to_lo + n * a.link_stride + (long long)j * nx + i, xv, L.tag0 + 2u);
+        if (LINK && DIM > 2 && k == 0 && L.has_lo) ll_store(L.to_lo + n * a.link_stride + (long long)j * nx + i, xv, L.tag0 + 2u);
       }
     }
     grid_barrier(a.tt.bar, gridDim.x, epoch);

@@ -492,6 +492,8 @@ static int solve_pressure(hg_state* s) {
       GsArgs a{}; a.CX = s->D; a.CY = s->CYs; a.CZ = s->CZs; a.RP = s->RP; a.PP = s->PP; a.diff = s->diffs; a.s_begin = sb; a.s_end = se;
       a.omega = c.lu_relaxed_relaxation_factor; a.tt = s->tt;
       a.link = slab_link(s, 0);
+      if (s->dim == 3 && s->world > 1) return s->any_excl ? coop_launch(s, k_gs_persistent<3, true, true>, s->grid_solver, s->geo, a, 0)
+                                                          : coop_launch(s, k_gs_persistent<3, false, true>, s->grid_solver, s->geo, a, 0);
       if (s->dim == 3) return s->any_excl ? coop_launch(s, k_gs_persistent<3, true>, s->grid_solver, s->geo, a, 0)
                                           : coop_launch(s, k_gs_persistent<3, false>, s->grid_solver, s->geo, a, 0);
       return s->any_excl ? coop_launch(s, k_gs_persistent<2, true>, s->grid_solver, s->geo, a, 0)
@@ -546,6 +548,7 @@ static int solve_lu(hg_state* s, int ncomp) {
   a.ncomp = ncomp; a.tt = s->tt;
   if (s->world > 1) ++s->slab.lu_seq;
   a.link = slab_link(s, 1); a.link_stride = s->nxy;
+  if (s->dim == 3 && s->world > 1) return coop_launch(s, k_lu_persistent<3, true>, s->grid_lu, s->geo, a, 1);
   if (s->dim == 3) return coop_launch(s, k_lu_persistent<3>, s->grid_lu, s->geo, a, 1);
   return coop_launch(s, k_lu_persistent<2>, s->grid_lu, s->geo, a, 1);
 }
