@@ -35,6 +35,19 @@ def workload_params(n):
     return cases.rt3d(n, fixed_work=True)
 
 
+def weak_mesh(n, world):
+    """Mesh of the weak-scaling run: n^3 cells per GPU; y, x, z are doubled in turn (2: n x 2n x n, 4: 2n x 2n x n,
+    8: 2n x 2n x 2n); other rank counts extend z."""
+    m = [n, n, n]
+    w, order, q = world, (1, 0, 2), 0
+    while w > 1 and w % 2 == 0:
+        m[order[q % 3]] *= 2
+        w //= 2
+        q += 1
+    m[2] *= w
+    return tuple(m)
+
+
 def bytes_per_cell_step(n_simple, sweeps_per_solve, n_adv, heat):
     """Algorithmic HBM bytes per cell per step, SURVEY.md 8(d) / BASELINE.md section 3."""
     return n_simple * (664 + 32 * sweeps_per_solve) + 96 * n_adv + (240 if heat else 0) + 120
@@ -145,9 +158,12 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     n = args.size
     p = workload_params(n)
+    mesh = weak_mesh(n, world)
     if world > 1:
-        # weak scaling: every rank owns an n^3 z-slab of an n x n x (n world) mesh with the same cell size
-        p.update(Nz=n * world, B=(1, 1, world), B1=(1, 0.5, world))
+        # weak scaling: n^3 cells per GPU, same cell size; z-slabs of a mesh that is kept as cubic as possible
+        # (the lexicographic sweeps are a wavefront over i+j+k: its length, nx+ny+nz, is the serial part)
+        fx, fy, fz = mesh[0] / n, mesh[1] / n, mesh[2] / n
+        p.update(Nx=mesh[0], Ny=mesh[1], Nz=mesh[2], B=(fx, fy, fz), B1=(fx, 0.5 * fy, fz))
         h = Hydro(p, device=local_rank, world_size=world, rank=rank)
         h.link_ipc(dist)
     else:
@@ -265,7 +281,7 @@ def run_b200(args, rank, local_rank, world):
                        "advection_substeps": n_adv,
                        "parallelism": "1 GPU" if world == 1 else
                        "z-slabs over %d GPUs, one process per GPU: %dx%dx%d cells, halo planes / solver interface values / "
-                       "reductions over NVLink peer memory (weak scaling, %d^3 cells per GPU)" % (world, n, n, n * world, n),
+                       "reductions over NVLink peer memory (weak scaling, %d^3 cells per GPU)" % ((world,) + mesh + (n,)),
                        "l2": "working set %.1f GB per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)" % (cells * 8 * 90 / 1e9)},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
     print(json.dumps(line))
