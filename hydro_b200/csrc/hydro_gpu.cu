@@ -45,6 +45,7 @@ struct hg_state {
   // time-skewed tile sweeps (hg_gs_tiled.cuh): explicit diagonal, task lists per number of sweeps in a launch
   bool gs_tiled = false;
   double* DGs = nullptr;
+  char* CO = nullptr; long long co_plane = 0, co_bytes = 0; int nxb = 0;   // packed rows of k_gs_tiled (gt_co_offset)
   struct GtPlan { int ntasks = 0; GtTask* tasks = nullptr; int* progress = nullptr; };
   std::map<int, GtPlan> gt_plans;
   int* gt_ctl = nullptr;
@@ -460,7 +461,7 @@ static int gt_plan(hg_state* s, int S, hg_state::GtPlan** out) {
 static int gt_launch(hg_state* s, int sb, int se, double omega) {
   hg_state::GtPlan* pl = nullptr;
   if (int rc = gt_plan(s, se - sb, &pl)) return rc;
-  GtArgs a; a.CX = s->D; a.CY = s->CYs; a.CZ = s->CZs; a.RP = s->RP; a.DG = s->DGs; a.PP = s->PP; a.diff = s->diffs;
+  GtArgs a; a.CO = s->CO; a.nxb = s->nxb; a.PSB = s->co_plane; a.PP = s->PP; a.diff = s->diffs;
   a.s_begin = sb; a.omega = omega; a.tasks = pl->tasks; a.ntasks = pl->ntasks; a.progress = pl->progress; a.ctl = s->gt_ctl;
   a.lag_prev = 2 * GT_B + 1;
   a.PS8 = 8LL * s->n[0] * s->n[1]; a.DSH8 = 8LL * (2LL * s->n[0] * s->n[1] + s->n[0] + 1);
@@ -747,6 +748,11 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
     DIMSEL(s, k_prhs, gb, 256, s->geo, s->Fs, s->dc, 0, s->An[0], s->An[1], s->An[2], s->An[3], s->gs_tiled ? s->An[4] : nullptr);
     double* outs[5] = {s->RP, s->D, s->CYs, s->CZs, s->DGs};
     shear_arrays(s, s->An, outs, s->gs_tiled ? 5 : 4);
+    if (s->gs_tiled) {
+      GtPackArgs pa; pa.RP = s->RP; pa.DG = s->DGs; pa.CX = s->D; pa.CY = s->CYs; pa.CZ = s->CZs; pa.CO = s->CO; pa.nxb = s->nxb;
+      k_gt_pack<<<dim3((s->n[0] + 31) / 32, (s->n[1] + 7) / 8, s->geo.np), 256, 0, s->st>>>(s->geo, pa);
+      ++s->launches;
+    }
     if (s->geo.zlo > 0) { k_cz_halo<3><<<nblk(s->nxy), 256, 0, s->st>>>(s->geo, s->dc, s->CZs); ++s->launches; }
   } else {
     DIMSEL(s, k_prhs, gb, 256, s->geo, s->Fs, s->dc, 1, s->RP, s->D, s->CYs, s->CZs, nullptr);
@@ -1119,7 +1125,14 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
       T.gs_tiled = dim == 3 && s->world == 1 && cfg->linear_solver_pressure == HG_LS_GAUSS_SEIDEL && !(e && !strcmp(e, "hyperplane")) &&
                    8LL * (GT_PAD + 2) * s->nxy < (1LL << 31);   // 32-bit byte offsets inside k_gs_tiled
     }
-    if (T.gs_tiled) T.DGs = take(s->nsh);
+    if (T.gs_tiled) {
+      T.nxb = (s->n[0] + 31) / 32;
+      T.co_plane = (long long)s->n[1] * T.nxb * GT_COBLK;
+      T.co_bytes = (long long)(s->geo.np + 2 * GT_PAD) * T.co_plane;
+      // 32-bit row offsets inside k_gs_tiled (gt_co_offset of planes <= GT_PAD)
+      if ((GT_PAD + 2) * T.co_plane >= (1LL << 32)) T.gs_tiled = false;
+    }
+    if (T.gs_tiled) { T.DGs = take(s->nsh); T.CO = (char*)take(T.co_bytes / 8); }
     // buffers peers read or write: exchange staging (2 parities x 2 directions x SLAB_MAX_ARRAYS x HG_HALO planes),
     // mailbox (2 parities x world x SLAB_MAIL doubles) and flag words
     if (s->world > 1) {
@@ -1148,7 +1161,9 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     if (dalloc(s, &s->gt_ctl, 4, true)) return fail_create(s, HG_ERR_CUDA, "allocation failed: " + s->err);
     // entry 0 of the sheared arrays (unused corner of the lower halo plane) is what threads without a cell read:
     // zero coefficients (set by the allocation), unit diagonal
-    { const double one = 1.; cudaMemcpyAsync(s->DGs, &one, sizeof(double), cudaMemcpyHostToDevice, s->st); cudaStreamSynchronize(s->st); }
+    { const long long nb = s->co_bytes / GT_COBLK;
+      k_gt_co_fill<<<nblk(nb * 128), 256, 0, s->st>>>((double2*)s->CO, nb);
+      if (cudaStreamSynchronize(s->st) != cudaSuccess) return fail_create(s, HG_ERR_CUDA, "k_gt_co_fill failed"); }
     if (cudaFuncSetAttribute(k_gs_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GT_SMEM_DOUBLES * sizeof(double))) != cudaSuccess)
       return fail_create(s, HG_ERR_CUDA, "k_gs_tiled: shared memory request rejected");
   }
