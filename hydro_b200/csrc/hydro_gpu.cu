@@ -45,7 +45,8 @@ struct hg_state {
   // time-skewed tile sweeps (hg_gs_tiled.cuh): explicit diagonal, task lists per number of sweeps in a launch
   bool gs_tiled = false;
   double* DGs = nullptr;
-  char* CO = nullptr; long long co_plane = 0, co_bytes = 0; int nxb = 0;   // packed rows of k_gs_tiled (gt_co_offset)
+  double2* CO = nullptr; long long co_n = 0;   // packed rows of k_gs_tiled (gt_co_index), co_n double2 per array
+  CUtensorMap tmco;
   struct GtPlan { int ntasks = 0; GtTask* tasks = nullptr; int* progress = nullptr; };
   std::map<int, GtPlan> gt_plans;
   int* gt_ctl = nullptr;
@@ -461,7 +462,7 @@ static int gt_plan(hg_state* s, int S, hg_state::GtPlan** out) {
 static int gt_launch(hg_state* s, int sb, int se, double omega) {
   hg_state::GtPlan* pl = nullptr;
   if (int rc = gt_plan(s, se - sb, &pl)) return rc;
-  GtArgs a; a.CO = s->CO; a.nxb = s->nxb; a.PSB = s->co_plane; a.PP = s->PP; a.diff = s->diffs;
+  GtArgs a; a.PP = s->PP; a.diff = s->diffs;
   a.s_begin = sb; a.omega = omega; a.tasks = pl->tasks; a.ntasks = pl->ntasks; a.progress = pl->progress; a.ctl = s->gt_ctl;
   a.lag_prev = 2 * GT_B + 1;
   a.PS8 = 8LL * s->n[0] * s->n[1]; a.DSH8 = 8LL * (2LL * s->n[0] * s->n[1] + s->n[0] + 1);
@@ -470,7 +471,7 @@ static int gt_launch(hg_state* s, int sb, int se, double omega) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (s->profile_on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s->st); }
   const int grid = std::min(pl->ntasks, s->num_sms);
-  k_gs_tiled<<<grid, GT_BLOCK, GT_SMEM_DOUBLES * sizeof(double), s->st>>>(s->geo, a);
+  k_gs_tiled<<<grid, GT_BLOCK, GT_SMEM_BYTES, s->st>>>(s->geo, a, s->tmco);
   CK(cudaGetLastError());
   if (e0) { cudaEventRecord(e1, s->st); s->prof_ev[0].push_back({e0, e1}); }
   ++s->launches;
@@ -749,7 +750,7 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
     double* outs[5] = {s->RP, s->D, s->CYs, s->CZs, s->DGs};
     shear_arrays(s, s->An, outs, s->gs_tiled ? 5 : 4);
     if (s->gs_tiled) {
-      GtPackArgs pa; pa.RP = s->RP; pa.DG = s->DGs; pa.CX = s->D; pa.CY = s->CYs; pa.CZ = s->CZs; pa.CO = s->CO; pa.nxb = s->nxb;
+      GtPackArgs pa; pa.RP = s->RP; pa.DG = s->DGs; pa.CX = s->D; pa.CY = s->CYs; pa.CZ = s->CZs; pa.CO = s->CO;
       k_gt_pack<<<dim3((s->n[0] + 31) / 32, (s->n[1] + 7) / 8, s->geo.np), 256, 0, s->st>>>(s->geo, pa);
       ++s->launches;
     }
@@ -1126,13 +1127,9 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
                    8LL * (GT_PAD + 2) * s->nxy < (1LL << 31);   // 32-bit byte offsets inside k_gs_tiled
     }
     if (T.gs_tiled) {
-      T.nxb = (s->n[0] + 31) / 32;
-      T.co_plane = (long long)s->n[1] * T.nxb * GT_COBLK;
-      T.co_bytes = (long long)(s->geo.np + 2 * GT_PAD) * T.co_plane;
-      // 32-bit row offsets inside k_gs_tiled (gt_co_offset of planes <= GT_PAD)
-      if ((GT_PAD + 2) * T.co_plane >= (1LL << 32)) T.gs_tiled = false;
+      T.co_n = (long long)(s->geo.np + 2 * GT_PAD) * s->nxy;
+      T.DGs = take(s->nsh); T.CO = (double2*)take(4 * T.co_n * 2);
     }
-    if (T.gs_tiled) { T.DGs = take(s->nsh); T.CO = (char*)take(T.co_bytes / 8); }
     // buffers peers read or write: exchange staging (2 parities x 2 directions x SLAB_MAX_ARRAYS x HG_HALO planes),
     // mailbox (2 parities x world x SLAB_MAIL doubles) and flag words
     if (s->world > 1) {
@@ -1161,10 +1158,24 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     if (dalloc(s, &s->gt_ctl, 4, true)) return fail_create(s, HG_ERR_CUDA, "allocation failed: " + s->err);
     // entry 0 of the sheared arrays (unused corner of the lower halo plane) is what threads without a cell read:
     // zero coefficients (set by the allocation), unit diagonal
-    { const long long nb = s->co_bytes / GT_COBLK;
-      k_gt_co_fill<<<nblk(nb * 128), 256, 0, s->st>>>((double2*)s->CO, nb);
-      if (cudaStreamSynchronize(s->st) != cudaSuccess) return fail_create(s, HG_ERR_CUDA, "k_gt_co_fill failed"); }
-    if (cudaFuncSetAttribute(k_gs_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GT_SMEM_DOUBLES * sizeof(double))) != cudaSuccess)
+    k_gt_co_fill<<<nblk(s->co_n), 256, 0, s->st>>>(s->CO, s->co_n);
+    if (cudaStreamSynchronize(s->st) != cudaSuccess) return fail_create(s, HG_ERR_CUDA, "k_gt_co_fill failed");
+    { // TMA descriptor of the packed rows: doubles [4][np + 2 GT_PAD][ny][2 nx], box = the rows of 32 cells
+      typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+      void* fn = nullptr; cudaDriverEntryPointQueryResult qr;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn)
+        return fail_create(s, HG_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+      const cuuint64_t nxd = 2ull * s->n[0], nyd = (cuuint64_t)s->n[1], npd = (cuuint64_t)(s->geo.np + 2 * GT_PAD);
+      const cuuint64_t dims[4] = {nxd, nyd, npd, 4};
+      const cuuint64_t strides[3] = {nxd * 8, nxd * 8 * nyd, nxd * 8 * nyd * npd};
+      const cuuint32_t box[4] = {64, 1, 1, 4}, estr[4] = {1, 1, 1, 1};
+      const CUresult r = ((EncodeFn)fn)(&s->tmco, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, s->CO, dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail_create(s, HG_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r)); }
+    if (cudaFuncSetAttribute(k_gs_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES) != cudaSuccess)
       return fail_create(s, HG_ERR_CUDA, "k_gs_tiled: shared memory request rejected");
   }
   int occ_gs = 0, occ_lu = 0;
