@@ -1,0 +1,196 @@
+// hg_lu_tiled.cuh -- the "lu" solver (LuDecomposition::Solve, linear.hpp:533-566): ONE lexicographic forward sweep
+//   x_i = (-c_i - sum_{j<i} a_ij x_j) / a_ii                 (linear.hpp:537-548)
+// and ONE backward sweep
+//   x_i -= (sum_{j>i} a_ij x_j) / a_ii                        (linear.hpp:551-563)
+// as a dataflow of column boxes instead of one grid barrier per hyperplane (k_lu_persistent, hg_solvers.cuh).
+//
+// A sweep only reads the three neighbours that come earlier in its order, so all cells of a hyperplane
+// S = i'+j'+k' are independent (primed = counted from the corner where the sweep starts: the backward sweep is the
+// forward sweep in mirrored indices).  A CTA owns a box of LT_TX x LT_TY columns and all k; thread (a,b) owns one
+// column and walks it one cell per step: at step S it updates k' = S - i' - j'.  Its z-neighbour is its own last
+// value (a register), the x- and y-neighbours were computed at step S-1 by the threads (a-1,b) and (a,b-1): they
+// are exchanged through a double-buffered shared-memory frame with one block barrier per step.  Values of the
+// boxes to the left and below arrive through the result array in global memory: a box publishes the number of
+// completed steps (release store) every LT_M steps, a dependent box polls it (acquire load) and then loads the halo
+// values of the next LT_M steps at once, so the critical path has one L2 round trip per LT_M hyperplanes instead
+// of a grid barrier per hyperplane.  Boxes are claimed from a list sorted by their first step, so a box only
+// waits for boxes claimed before it.
+//
+// The arithmetic (term order z, y, x; one division per component) is that of k_lu_persistent: bit-identical.
+#pragma once
+#include "hg_device.cuh"
+
+constexpr int LT_TX = 32, LT_TY = 16, LT_M = 8, LT_PF = 4;   // LT_M % LT_PF == 0: operand slots are compile-time
+constexpr int LT_THREADS = LT_TX * LT_TY;
+constexpr int LT_FW = LT_TX + 1, LT_FH = LT_TY + 1, LT_FRAME = LT_FW * LT_FH;   // frame: halo column / row at index 0
+constexpr int LT_HALO = LT_TX + LT_TY;            // halo entries per frame: column 0 (rows 1..TY), row 0 (columns 1..TX)
+constexpr int LT_PBIAS = 1;
+
+struct LtArgs {
+  const double* A[7];   // sheared rows
+  const double* R[3];   // sheared constants (forward sweep)
+  double* X[3];         // sheared result: written by the forward sweep, updated in place by the backward sweep
+  int ncomp;
+  const int2* boxes;    // (I', J') in claim order
+  int nboxes, nbi;      // boxes, boxes along i
+  int* progress;        // [nboxes] completed steps + LT_PBIAS, indexed J' * nbi + I'; zeroed before the launch
+  int* ctl;             // [0] next box, [1] abort flag
+};
+
+DV int lt_ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+DV void lt_st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// DIR = 0: forward sweep, DIR = 1: backward sweep
+template <int DIR>
+__global__ void __launch_bounds__(LT_THREADS, 1) k_lu_tiled(Geo g, LtArgs a) {
+  __shared__ double fr[2][3][LT_FRAME];            // values of the last two steps
+  __shared__ double stage[LT_M][3][LT_HALO];       // halo values of the LT_M steps of a macro step
+  __shared__ int s_box;
+  const int tid = threadIdx.x, ta = tid & (LT_TX - 1), tb = tid / LT_TX;
+  const int nx = g.n[0], ny = g.n[1], nz = g.n[2];
+  const long long PS = (long long)nx * ny;
+  const long long sgn = DIR ? -1 : 1;              // a step moves the thread by one hyperplane: +PS / -PS entries
+  const long long nbx = sgn * (PS + 1), nby = sgn * (PS + nx), nbz = sgn * PS;   // cs - nb* = the earlier neighbour
+  // coefficient slots: diagonal + the three earlier neighbours
+  const double* const Az = a.A[DIR ? CZP : CZM];
+  const double* const Ay = a.A[DIR ? CYP : CYM];
+  const double* const Ax = a.A[DIR ? CXP : CXM];
+  const double* const Ad = a.A[CD];
+  // components beyond ncomp alias component 0 (loaded, never stored): no conditional loads in the step loop
+  const double* src[3]; double* dstx[3];
+#pragma unroll
+  for (int n = 0; n < 3; ++n) { const int q = n < a.ncomp ? n : 0; src[n] = DIR ? a.X[q] : a.R[q]; dstx[n] = a.X[q]; }
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_box = atomicAdd(&a.ctl[0], 1);
+    __syncthreads();
+    const int t = s_box;
+    if (t >= a.nboxes || *(volatile int*)&a.ctl[1]) return;
+    const int2 bx = a.boxes[t];
+    const int I0 = bx.x * LT_TX, J0 = bx.y * LT_TY;
+    const int ip = I0 + ta, jp = J0 + tb;                      // primed column
+    const bool col = ip < nx && jp < ny;
+    const int i = DIR ? nx - 1 - ip : ip, j = DIR ? ny - 1 - jp : jp;
+    const int Slo = I0 + J0;
+    const int Shi = min(I0 + LT_TX, nx) - 1 + min(J0 + LT_TY, ny) - 1 + nz - 1;
+    const int nmacro = (Shi - Slo + LT_M) / LT_M;
+    const int me = bx.y * a.nbi + bx.x;
+    const int dep_x = bx.x > 0 ? me - 1 : -1, dep_y = bx.y > 0 ? me - a.nbi : -1;
+    for (int q = tid; q < 2 * 3 * LT_FRAME; q += LT_THREADS) (&fr[0][0][0])[q] = 0.;
+    for (int q = tid; q < LT_M * 3 * LT_HALO; q += LT_THREADS) (&stage[0][0][0])[q] = 0.;
+    // sheared index of the thread's cell at step S: plane (S + 1) forward, (np - S) backward (np - 1 = largest i+j+k)
+    long long cs = DIR ? ((long long)(g.np - Slo) * ny + j) * nx + i : ((long long)(Slo + 1) * ny + j) * nx + i;
+    // neighbour existence as the reference tests it (k_lu_persistent)
+    const bool hx = DIR ? i + 1 < nx : i > 0, hy = DIR ? j + 1 < ny : j > 0;
+    double xz[3] = {0., 0., 0.};                               // own value of the previous step
+    // operands LT_PF steps ahead
+    double pz[LT_PF], py[LT_PF], px[LT_PF], pd[LT_PF], pr[LT_PF][3];
+    // threads without a cell at that step read entry 0 of the arrays (an unused corner entry) and their result is
+    // discarded: unconditional loads, issued back to back
+    auto load_ops = [&](int slot, long long c, int S) {
+      const int kp = S - ip - jp;
+      const bool v = col && kp >= 0 && kp < nz;
+      if (!v) c = 0;
+      pz[slot] = Az[c]; py[slot] = Ay[c]; px[slot] = Ax[c]; pd[slot] = v ? Ad[c] : 1.;
+#pragma unroll
+      for (int n = 0; n < 3; ++n) pr[slot][n] = __ldcg(&src[n][c]);
+    };
+#pragma unroll
+    for (int q = 0; q < LT_PF; ++q) load_ops(q, cs + q * nbz, Slo + q);
+    double* const f0 = &fr[0][0][0] + (tb + 1) * LT_FW + ta + 1;   // own slot in frame 0, component 0
+    __syncthreads();
+    for (int m = 0; m < nmacro; ++m) {
+      const int S0 = Slo + m * LT_M;
+      // ---- halo values of steps S0 .. S0+M-1 (hyperplanes S0-1 .. S0+M-2 of the neighbouring boxes)
+      if (dep_x >= 0 || dep_y >= 0) {
+        if (tid < 2) {
+          const int dep = tid == 0 ? dep_x : dep_y;
+          if (dep >= 0) {
+            const int need = S0 + LT_M - 1 + LT_PBIAS;
+            long long t0 = 0;
+            for (unsigned spins = 0; lt_ld_acquire(&a.progress[dep]) < need; ++spins) {
+              if ((spins & 0xff) == 0xff) {   // bounded wait: a scheduling bug must not hang the device
+                const long long now = clock64();
+                if (t0 == 0) t0 = now;
+                if (now - t0 > 4000000000LL) atomicExch(&a.ctl[1], 1);
+                if (*(volatile int*)&a.ctl[1]) break;
+              }
+            }
+          }
+        }
+        __syncthreads();
+        // entry e of a frame's halo: e < TY: column 0, row e+1 (x-neighbour of thread (0, e)); else row 0, column e-TY+1
+        for (int q = tid; q < LT_M * LT_HALO; q += LT_THREADS) {
+          const int st = q / LT_HALO, e = q - st * LT_HALO;
+          const bool isx = e < LT_TY;
+          const int qa = isx ? 0 : e - LT_TY, qb = isx ? e : 0;          // the thread whose neighbour this is
+          const int qip = I0 + qa, qjp = J0 + qb;
+          const int S = S0 + st, kp = S - qip - qjp;
+          const bool v = (isx ? dep_x >= 0 : dep_y >= 0) && qip < nx && qjp < ny && kp >= 0 && kp < nz;
+          const int qi = DIR ? nx - 1 - qip : qip, qj = DIR ? ny - 1 - qjp : qjp;
+          long long c = (DIR ? ((long long)(g.np - S) * ny + qj) * nx + qi : ((long long)(S + 1) * ny + qj) * nx + qi) - (isx ? nbx : nby);
+          if (!v) c = 0;
+          double hvv[3];
+#pragma unroll
+          for (int n = 0; n < 3; ++n) hvv[n] = __ldcg(&dstx[n][c]);
+#pragma unroll
+          for (int n = 0; n < 3; ++n) stage[st][n][e] = v ? hvv[n] : 0.;
+        }
+        __syncthreads();
+      }
+      // ---- LT_M steps
+#pragma unroll
+      for (int st = 0; st < LT_M; ++st) {
+        const int S = S0 + st, par = S & 1;
+        const int kp = S - ip - jp;
+        const bool v = col && kp >= 0 && kp < nz;
+        const int k = DIR ? nz - 1 - kp : kp;
+        const bool hz = DIR ? k + 1 < nz : k > 0;
+        const int slot = st % LT_PF;
+        const double cz = pz[slot], cy = py[slot], cx = px[slot], dg = pd[slot];
+        double rr[3];
+#pragma unroll
+        for (int n = 0; n < 3; ++n) rr[n] = pr[slot][n];
+        load_ops(slot, cs + LT_PF * nbz, S + LT_PF);
+        // halo of the frame of step S-1 for this step's edge threads
+        if (tid < LT_HALO) {
+#pragma unroll
+          for (int n = 0; n < 3; ++n) {
+            const int e = tid;
+            double* const dst = &fr[par ^ 1][n][0] + (e < LT_TY ? (e + 1) * LT_FW : e - LT_TY + 1);
+            *dst = stage[st][n][e];
+          }
+        }
+        __syncthreads();
+        double* const fprev = f0 + (par ^ 1) * 3 * LT_FRAME;
+        double* const fcur = f0 + par * 3 * LT_FRAME;
+#pragma unroll
+        for (int n = 0; n < 3; ++n) {
+          double xv = 0.;
+          if (n < a.ncomp) {
+            const double vx = fprev[n * LT_FRAME - 1], vy = fprev[n * LT_FRAME - LT_FW];
+            double sum = 0.;
+            if (hz) sum += cz * xz[n];
+            if (hy) sum += cy * vy;
+            if (hx) sum += cx * vx;
+            xv = DIR ? rr[n] - sum / dg : (-rr[n] - sum) / dg;
+            if (v) a.X[n][cs] = xv; else xv = 0.;
+          }
+          fcur[n * LT_FRAME] = xv;
+          xz[n] = xv;
+        }
+        cs += nbz;
+      }
+      // ---- publish: steps < S0 + M are complete
+      __syncthreads();
+      if (tid == 0) lt_st_release(&a.progress[me], S0 + LT_M + LT_PBIAS);
+    }
+    if (tid == 0) lt_st_release(&a.progress[me], 0x7fffffff);
+  }
+}

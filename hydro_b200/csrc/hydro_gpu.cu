@@ -18,6 +18,7 @@
 #include "hg_solvers.cuh"
 #include "hg_slab.cuh"
 #include "hg_gs_tiled.cuh"
+#include "hg_lu_tiled.cuh"
 
 enum { L_TC = 0, L_TP = 1, L_IC = 2, L_IP = 3 };
 
@@ -50,6 +51,8 @@ struct hg_state {
   struct GtPlan { int ntasks = 0; GtTask* tasks = nullptr; int* progress = nullptr; };
   std::map<int, GtPlan> gt_plans;
   int* gt_ctl = nullptr;
+  // lu as a dataflow of column boxes (hg_lu_tiled.cuh)
+  bool lu_tiled = false; int2* lt_boxes = nullptr; int lt_nboxes = 0, lt_nbi = 0; int* lt_progress = nullptr; int* lt_ctl = nullptr;
   int num_sms = 0;
   double* resid = nullptr;    // per-iteration convergence indicators of the current step (device, 4096)
   double* scal = nullptr;     // device scalars: [0] resid, [1] auto dt, [2..] stat (36), then diffs
@@ -485,6 +488,7 @@ static int gt_check(hg_state* s) {   // after the sweeps: did a dependency wait 
   return 0;
 }
 
+static int lt_check(hg_state* s);
 static int solve_pressure(hg_state* s) {
   const hg_config& c = s->cfg;
   int it = 0; double df = 0.;
@@ -503,6 +507,7 @@ static int solve_pressure(hg_state* s) {
     };
     if (int rc = run_sor(s, s->PP, s->nsh, c.lu_relaxed_tolerance, c.lu_relaxed_num_iters_limit, launch, &it, &df)) return rc;
     if (s->gs_tiled) if (int rc = gt_check(s)) return rc;
+    if (s->lu_tiled) if (int rc = lt_check(s)) return rc;
     DIMSEL(s, k_pcorr, nblk(s->nc), 256, s->geo, s->PP, s->p[L_IP], c.pressure_relaxation_factor, s->pc, s->p[L_IC]);
   } else if (c.linear_solver_pressure == HG_LS_JACOBI) {
     // natural layout: constants back from the sheared array, rows regenerated from d_c
@@ -543,7 +548,35 @@ static int shear_arrays(hg_state* s, double* const* in, double* const* out, int 
   return 0;
 }
 
+static int solve_lu_tiled(hg_state* s, int ncomp) {
+  LtArgs a{};
+  for (int t = 0; t < 7; ++t) a.A[t] = s->A[t];
+  for (int n = 0; n < 3; ++n) { a.R[n] = s->R[n]; a.X[n] = s->X[n]; }
+  a.ncomp = ncomp; a.boxes = s->lt_boxes; a.nboxes = s->lt_nboxes; a.nbi = s->lt_nbi; a.progress = s->lt_progress; a.ctl = s->lt_ctl;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (s->profile_on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s->st); }
+  const int grid = std::min(s->lt_nboxes, s->num_sms);
+  for (int dir = 0; dir < 2; ++dir) {
+    CK(cudaMemsetAsync(s->lt_progress, 0, s->lt_nboxes * sizeof(int), s->st));
+    CK(cudaMemsetAsync(s->lt_ctl, 0, sizeof(int), s->st));   // next-box counter; the abort flag [1] is sticky
+    if (dir == 0) k_lu_tiled<0><<<grid, LT_THREADS, 0, s->st>>>(s->geo, a);
+    else k_lu_tiled<1><<<grid, LT_THREADS, 0, s->st>>>(s->geo, a);
+    CK(cudaGetLastError());
+    ++s->launches;
+  }
+  if (e0) { cudaEventRecord(e1, s->st); s->prof_ev[1].push_back({e0, e1}); }
+  return 0;
+}
+static int lt_check(hg_state* s) {   // did a dependency wait time out?
+  int h = 0;
+  CK(cudaMemcpyAsync(&h, s->lt_ctl + 1, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+  CK(cudaStreamSynchronize(s->st));
+  if (h) { s->err = "k_lu_tiled: dependency wait timed out"; return HG_ERR_CUDA; }
+  return 0;
+}
+
 static int solve_lu(hg_state* s, int ncomp) {
+  if (s->lu_tiled) return solve_lu_tiled(s, ncomp);
   LuArgs a{};
   for (int t = 0; t < 7; ++t) a.A[t] = s->A[t];
   for (int n = 0; n < 3; ++n) { a.R[n] = s->R[n]; a.X[n] = s->X[n]; }
@@ -1177,6 +1210,19 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
       if (r != CUDA_SUCCESS) return fail_create(s, HG_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r)); }
     if (cudaFuncSetAttribute(k_gs_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES) != cudaSuccess)
       return fail_create(s, HG_ERR_CUDA, "k_gs_tiled: shared memory request rejected");
+  }
+  { const char* e = getenv("HYDRO_LU_KERNEL");
+    s->lu_tiled = dim == 3 && s->world == 1 && !(e && !strcmp(e, "hyperplane")); }
+  if (s->lu_tiled) {
+    const int nbi = (s->n[0] + LT_TX - 1) / LT_TX, nbj = (s->n[1] + LT_TY - 1) / LT_TY;
+    std::vector<int2> boxes;
+    for (int J = 0; J < nbj; ++J) for (int I = 0; I < nbi; ++I) boxes.push_back(make_int2(I, J));
+    std::stable_sort(boxes.begin(), boxes.end(), [](const int2& p, const int2& q) { return p.x * LT_TX + p.y * LT_TY < q.x * LT_TX + q.y * LT_TY; });
+    s->lt_nboxes = (int)boxes.size(); s->lt_nbi = nbi;
+    if (dalloc(s, &s->lt_boxes, s->lt_nboxes, false) || dalloc(s, &s->lt_progress, s->lt_nboxes, true) || dalloc(s, &s->lt_ctl, 4, true))
+      return fail_create(s, HG_ERR_CUDA, "allocation failed: " + s->err);
+    cudaMemcpyAsync(s->lt_boxes, boxes.data(), boxes.size() * sizeof(int2), cudaMemcpyHostToDevice, s->st);
+    cudaStreamSynchronize(s->st);
   }
   int occ_gs = 0, occ_lu = 0;
   if (dim == 3) {
