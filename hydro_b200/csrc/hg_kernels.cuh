@@ -284,15 +284,16 @@ __global__ void k_assemble(Geo g, AsmArgs a) {
     }
   }
   const double r = a.rho ? a.rho[c] : 1.;
+  const HgDiv dvol = hg_div_prepare(g.vol);   // ~20 divisions by the cell volume per cell
   double coef[7] = {0, 0, 0, 0, 0, 0, 0};
-  coef[CD] = ((have_c ? cdiag / g.vol : 0.) + a.co[2]) * r + (have_d ? ddiag / g.vol : 0.);
+  coef[CD] = ((have_c ? hg_div(cdiag, dvol) : 0.) + a.co[2]) * r + (have_d ? hg_div(ddiag, dvol) : 0.);
 #pragma unroll
-  for (int q = 0; q < 2 * DIM; ++q) if (present[q]) coef[tmap[q]] = (cn[q] / g.vol) * r + dn[q] / g.vol;
+  for (int q = 0; q < 2 * DIM; ++q) if (present[q]) coef[tmap[q]] = hg_div(cn[q], dvol) * r + hg_div(dn[q], dvol);
   // delta form: constant := eqn.Evaluate(prev) in ascending index order (conv_diff.hpp:218)
 #pragma unroll
   for (int n = 0; n < NCOMP; ++n) {
     const double uconst = a.co[0] * a.tp[n][c] + a.co[1] * a.tc[n][c];
-    double ev = ((cconst[n] / g.vol + uconst) * r + dconst[n] / g.vol) - a.src[n][c];
+    double ev = ((hg_div(cconst[n], dvol) + uconst) * r + hg_div(dconst[n], dvol)) - a.src[n][c];
 #pragma unroll
     for (int t = 0; t < 7; ++t) {
       if (DIM == 2 && (t == CZM || t == CZP)) continue;

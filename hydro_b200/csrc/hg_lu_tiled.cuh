@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_lu_tiled(Geo g, LtArgs a) {
         const bool hz = DIR ? k + 1 < nz : k > 0;
         const int slot = st % LT_PF;
         const double cz = pz[slot], cy = py[slot], cx = px[slot], dg = pd[slot];
+        const HgDiv ddg = hg_div_prepare(dg);   // one reciprocal for the components
         double rr[3];
 #pragma unroll
         for (int n = 0; n < 3; ++n) rr[n] = pr[slot][n];
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_lu_tiled(Geo g, LtArgs a) {
             if (hz) sum += cz * xz[n];
             if (hy) sum += cy * vy;
             if (hx) sum += cx * vx;
-            xv = DIR ? rr[n] - sum / dg : (-rr[n] - sum) / dg;
+            xv = DIR ? rr[n] - hg_div(sum, ddg) : hg_div(-rr[n] - sum, ddg);
             if (v) a.X[n][cs] = xv; else xv = 0.;
           }
           fcur[n * LT_FRAME] = xv;
