@@ -249,7 +249,7 @@ def run_b200(args, rank, local_rank, world):
     achieved = gs_bytes / (gs_avg_ms * 1e-3) / 1e9 if gs_n else None
     bpcs = bytes_per_cell_step(n_simple, sweeps_per_solve, n_adv, False)
     step_gbs = bpcs * cells / sec_step / 1e9
-    kname = ("k_gs_tiled (lexicographic Gauss-Seidel/SOR as time-skewed tile dataflow, %d sweeps per launch)" if world == 1 else
+    kname = ("k_gs_tiled (lexicographic Gauss-Seidel/SOR as time-skewed column boxes, rows staged by TMA, %d sweeps per launch)" if world == 1 else
              "k_gs_persistent<3> (lexicographic Gauss-Seidel/SOR, hyperplanes linked across the slabs, %d sweeps per launch)")
     roof = {"bound": "hbm", "kernel": kname % sweeps_per_solve,
             "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",

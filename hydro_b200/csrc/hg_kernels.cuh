@@ -10,13 +10,22 @@
 
 namespace cg = cooperative_groups;
 
+// thread -> cell (i, j, k), raw index c (mesh.hpp:552-561).  32-bit divisions when the mesh allows it (64-bit
+// division / modulo costs a few hundred instructions per thread, comparable to a whole stencil kernel body).
 #define CELL_LOOP_PROLOG(g)                                                   \
   long long c_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;            \
   long long nc_ = (long long)(g).n[0] * (g).n[1] * (g).n[2];                  \
   if (c_ >= nc_) return;                                                      \
-  int i = (int)(c_ % (g).n[0]);                                               \
-  int j = (int)((c_ / (g).n[0]) % (g).n[1]);                                  \
-  int k = (int)(c_ / ((long long)(g).n[0] * (g).n[1]));                       \
+  int i, j, k;                                                                \
+  if (nc_ < (1LL << 31)) {                                                    \
+    const unsigned c32_ = (unsigned)c_, nx_ = (unsigned)(g).n[0], nxy_ = nx_ * (unsigned)(g).n[1]; \
+    const unsigned k_ = c32_ / nxy_, r_ = c32_ - k_ * nxy_, j_ = r_ / nx_;    \
+    k = (int)k_; j = (int)j_; i = (int)(r_ - j_ * nx_);                       \
+  } else {                                                                    \
+    i = (int)(c_ % (g).n[0]);                                                 \
+    j = (int)((c_ / (g).n[0]) % (g).n[1]);                                    \
+    k = (int)(c_ / ((long long)(g).n[0] * (g).n[1]));                         \
+  }                                                                           \
   const long long c = c_;
 
 struct P3 { double* p[3]; };
