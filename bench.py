@@ -218,15 +218,21 @@ def run_b200(args, rank, local_rank, world):
     for k in ins:
         h.get_to(k, pin_in[k].data_ptr())
     Ke = max(2, min(K, 3))
+    for k in ins:    # untimed: first use allocates the staging / snapshot buffers and the copy streams
+        h.set_from_async(k, pin_in[k].data_ptr())
+    for k in outs:
+        h.get_to_async(k, pin_out[k].data_ptr())
     barrier()
     t0 = time.perf_counter()
     for _ in range(Ke):
+        # uploads go through a copy stream into staging buffers and are applied in stream order before the step; the
+        # downloads copy a snapshot taken after the step and overlap the next step (hg_*_field_async, pinned buffers)
         for k in ins:
-            h.set_from(k, pin_in[k].data_ptr())
+            h.set_from_async(k, pin_in[k].data_ptr())
         st2 = h.step()
         for k in outs:
-            h.get_to(k, pin_out[k].data_ptr())
-    barrier()
+            h.get_to_async(k, pin_out[k].data_ptr())
+    barrier()   # hg_device_synchronize waits for the compute and both copy streams
     e2e_sec = (time.perf_counter() - t0) / Ke
     if dist is not None:
         t = torch.tensor([e2e_sec], dtype=torch.float64, device="cuda")
@@ -234,7 +240,8 @@ def run_b200(args, rank, local_rank, world):
         e2e_sec = float(t.item())
     e2e = {"value": world * cells / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": len(ins) * cells * 8,
            "d2h_bytes_per_step": len(outs) * cells * 8 + 8 * 40, "ms_per_step": e2e_sec * 1e3, "steps": Ke,
-           "timing": "host wall clock around pinned H2D + hg_step + D2H, stream-synchronised, max over ranks"}
+           "timing": "host wall clock around pinned H2D (hg_set_field_async) + hg_step + D2H (hg_get_field_async), all streams "
+                     "synchronised at the end, max over ranks"}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

@@ -20,7 +20,7 @@ _lib = None
 
 SYMBOLS = [
     "hg_config_defaults", "hg_create", "hg_destroy", "hg_last_error", "hg_num_cells", "hg_num_faces",
-    "hg_set_field", "hg_get_field", "hg_step", "hg_run", "hg_fluid_start_step", "hg_fluid_make_iteration",
+    "hg_set_field", "hg_get_field", "hg_set_field_async", "hg_get_field_async", "hg_step", "hg_run", "hg_fluid_start_step", "hg_fluid_make_iteration",
     "hg_fluid_convergence_indicator", "hg_fluid_is_converged", "hg_last_residuals", "hg_fluid_finish_step",
     "hg_fluid_auto_time_step", "hg_set_time_step", "hg_advection_step", "hg_heat_step",
     "hg_update_properties", "hg_calc_stat", "hg_interp_grad", "hg_linear_solve", "hg_smooth_field",
@@ -50,6 +50,8 @@ def load_library():
     l.hg_num_faces.restype = C.c_size_t
     l.hg_set_field.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t]
     l.hg_get_field.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t]
+    l.hg_set_field_async.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t]
+    l.hg_get_field_async.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t]
     l.hg_step.argtypes = [C.c_void_p, C.POINTER(HgStepStats)]
     l.hg_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(HgStepStats)]
     for n in ("hg_fluid_start_step", "hg_fluid_make_iteration", "hg_fluid_finish_step", "hg_advection_step",
@@ -276,6 +278,16 @@ class Hydro:
     def get_to(self, name, ptr):
         fid = F[name] if isinstance(name, str) else name
         self._chk(self.l.hg_get_field(self.h, fid, C.cast(ptr, C.POINTER(C.c_double)), self.nf if fid in FACE_FIELDS else self.nc))
+
+    def set_from_async(self, name, ptr):
+        """hg_set_field_async from a raw PINNED host pointer; complete after synchronize()."""
+        fid = F[name] if isinstance(name, str) else name
+        self._chk(self.l.hg_set_field_async(self.h, fid, C.cast(ptr, C.POINTER(C.c_double)), self.nf if fid in FACE_FIELDS else self.nc))
+
+    def get_to_async(self, name, ptr):
+        """hg_get_field_async into a raw PINNED host pointer; valid after synchronize()."""
+        fid = F[name] if isinstance(name, str) else name
+        self._chk(self.l.hg_get_field_async(self.h, fid, C.cast(ptr, C.POINTER(C.c_double)), self.nf if fid in FACE_FIELDS else self.nc))
 
     def launch_count(self):
         return int(self.l.hg_launch_count(self.h))

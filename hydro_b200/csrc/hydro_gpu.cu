@@ -28,6 +28,10 @@ struct hg_state {
   hg_config cfg;
   int dev = 0;
   cudaStream_t st = nullptr;
+  // asynchronous field transfers (hg_set_field_async / hg_get_field_async): copy streams, staging / snapshot buffers per field
+  cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
+  std::map<int, double*> xfer_stage, xfer_snap;
+  std::map<int, cudaEvent_t> xfer_ev;
   int dim = 0, n[3] = {1, 1, 1};
   long long nc = 0, nf = 0, nsh = 0;
   Geo geo;
@@ -1407,6 +1411,9 @@ extern "C" int hg_destroy(hg_handle s) {
   if (s->hdiffs) cudaFreeHost(s->hdiffs);
   for (auto& kv : s->timers) { if (kv.second.a) { cudaEventDestroy(kv.second.a); cudaEventDestroy(kv.second.b); } }
   cudaStreamDestroy(s->st);
+  if (s->st_h2d) cudaStreamDestroy(s->st_h2d);
+  if (s->st_d2h) cudaStreamDestroy(s->st_d2h);
+  for (auto& e : s->xfer_ev) cudaEventDestroy(e.second);
   delete s;
   return 0;
 }
@@ -1419,6 +1426,8 @@ extern "C" int hg_device_synchronize(hg_handle s) {
   if (!s) return HG_ERR_INVALID;
   cudaSetDevice(s->dev);
   CK(cudaStreamSynchronize(s->st));
+  if (s->st_h2d) CK(cudaStreamSynchronize(s->st_h2d));
+  if (s->st_d2h) CK(cudaStreamSynchronize(s->st_d2h));
   return 0;
 }
 
@@ -1453,6 +1462,70 @@ extern "C" int hg_set_field(hg_handle s, int field, const double* src, size_t n)
     CK(cudaMemcpyAsync(q, src, n * sizeof(double), cudaMemcpyHostToDevice, s->st));
   }
   CK(cudaStreamSynchronize(s->st));
+  return 0;
+}
+
+// Asynchronous transfers for callers that keep their buffers in pinned memory and overlap the copies with the
+// time step (the module-owned property fields go in before a step, results come out after it, hydro2d.hpp:449-463).
+// set: the upload runs on its own stream into a staging buffer; the compute stream copies it into the field (and its
+// previous-time layer, like hg_set_field) once it has arrived, so a step that is still running is never disturbed.
+// get: the compute stream takes a snapshot of the field when it reaches this point; the download of the snapshot runs
+// on its own stream, concurrently with the next step.  hg_device_synchronize waits for all of it.
+static int xfer_setup(hg_state* s, int field, long long m, std::map<int, double*>& bufs, double** out) {
+  if (!s->st_h2d) {
+    CK(cudaStreamCreateWithFlags(&s->st_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s->st_d2h, cudaStreamNonBlocking));
+  }
+  auto it = bufs.find(field);
+  if (it == bufs.end()) {
+    double* q = nullptr;
+    if (int rc = dalloc(s, &q, m, false)) return rc;
+    it = bufs.emplace(field, q).first;
+  }
+  *out = it->second;
+  return 0;
+}
+extern "C" int hg_set_field_async(hg_handle s, int field, const double* src, size_t n) {
+  if (!s || !src) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  long long m; double* p = field_ptr(s, field, L_TC, &m);
+  if (!p || (long long)n != m || field == HG_F_EXCLUDED) { s->err = "hg_set_field_async: bad field id or size"; return HG_ERR_INVALID; }
+  double* stage = nullptr;
+  if (int rc = xfer_setup(s, field, m, s->xfer_stage, &stage)) return rc;
+  cudaEvent_t ev = nullptr;
+  CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CK(cudaEventRecord(ev, s->st)); CK(cudaStreamWaitEvent(s->st_h2d, ev, 0));   // the staging buffer's last consumer is done
+  CK(cudaMemcpyAsync(stage, src, n * sizeof(double), cudaMemcpyHostToDevice, s->st_h2d));
+  CK(cudaEventRecord(ev, s->st_h2d)); CK(cudaStreamWaitEvent(s->st, ev, 0));
+  CK(cudaEventDestroy(ev));
+  CK(cudaMemcpyAsync(p, stage, n * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
+  if (field <= HG_F_TEMPERATURE) {
+    double* q = field_ptr(s, field, L_TP, &m);
+    CK(cudaMemcpyAsync(q, stage, n * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
+  }
+  return 0;
+}
+extern "C" int hg_get_field_async(hg_handle s, int field, double* dst, size_t n) {
+  if (!s || !dst) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  long long m; double* p = field_ptr(s, field, L_TC, &m);
+  if (!p || (long long)n != m || field == HG_F_EXCLUDED) { s->err = "hg_get_field_async: bad field id or size"; return HG_ERR_INVALID; }
+  double* snap = nullptr;
+  if (int rc = xfer_setup(s, field, m, s->xfer_snap, &snap)) return rc;
+  auto it = s->xfer_ev.find(field);
+  if (it == s->xfer_ev.end()) {
+    cudaEvent_t e = nullptr; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    it = s->xfer_ev.emplace(field, e).first;
+  } else {
+    CK(cudaStreamWaitEvent(s->st, it->second, 0));   // the previous download of this snapshot has finished
+  }
+  CK(cudaMemcpyAsync(snap, p, n * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
+  cudaEvent_t ev = nullptr;
+  CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CK(cudaEventRecord(ev, s->st)); CK(cudaStreamWaitEvent(s->st_d2h, ev, 0));
+  CK(cudaEventDestroy(ev));
+  CK(cudaMemcpyAsync(dst, snap, n * sizeof(double), cudaMemcpyDeviceToHost, s->st_d2h));
+  CK(cudaEventRecord(it->second, s->st_d2h));
   return 0;
 }
 

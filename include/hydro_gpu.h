@@ -190,6 +190,12 @@ size_t hg_num_faces(hg_handle h);
  * time_prev layers, as the solvers' constructors do (conv_diff.hpp:113-114). */
 int hg_set_field(hg_handle h, int field, const double* src, size_t n);
 int hg_get_field(hg_handle h, int field, double* dst, size_t n);
+/* Asynchronous variants for PINNED host buffers (same ids, sizes and semantics; the module-owned property fields of
+ * hydro2d.hpp:449-463 go in before a step, results come out after it).  The upload runs on a copy stream into a staging
+ * buffer and is applied when the compute stream reaches the call's position; the download copies a snapshot taken at the
+ * call's position, concurrently with later steps.  The host buffer may be reused / read after hg_device_synchronize. */
+int hg_set_field_async(hg_handle h, int field, const double* src, size_t n);
+int hg_get_field_async(hg_handle h, int field, double* dst, size_t n);
 
 /* one whole time step = hydro<Mesh>::step() (hydro2d.hpp:1531-1621) */
 int hg_step(hg_handle h, hg_step_stats* stats /* may be NULL */);

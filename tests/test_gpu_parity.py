@@ -276,3 +276,29 @@ def test_set_get_roundtrip_and_idempotent_properties():
     a = h.get("DENSITY").copy()
     h.update_properties()
     assert np.array_equal(h.get("DENSITY"), a)
+
+
+def test_async_field_transfers_equal_blocking_ones():
+    """hg_set_field_async / hg_get_field_async (pinned buffers, copy streams) against hg_set_field / hg_get_field."""
+    import torch
+    from hydro_b200.capi import Hydro
+    p = cases.rt3d(12)
+    a, b = Hydro(p), Hydro(p)
+    a.step(), b.step()
+    names_in = ["DENSITY", "VISCOSITY", "FORCE_Y"]
+    names_out = ["VELOCITY_X", "VELOCITY_Y", "VELOCITY_Z", "PRESSURE"]
+    rng = np.random.default_rng(3)
+    pins = {n: torch.empty(a.nc, dtype=torch.float64).pin_memory() for n in names_in + names_out}
+    for it in range(3):
+        for n in names_in:
+            v = a.get(n) * (1. + 1e-3 * rng.standard_normal(a.nc))
+            a.set(n, v)
+            pins[n].numpy()[:] = v
+            b.set_from_async(n, pins[n].data_ptr())
+        a.step(), b.step()
+        for n in names_out:
+            b.get_to_async(n, pins[n].data_ptr())
+        b.synchronize()
+        for n in names_out:
+            assert np.array_equal(pins[n].numpy(), a.get(n)), (it, n)
+    a.close(), b.close()
