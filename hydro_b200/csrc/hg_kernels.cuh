@@ -5,6 +5,7 @@
 // materialises a FieldFace for every Interpolate call).  Each kernel cites the reference
 // code it replaces; the arithmetic order follows oracle/hydro_oracle.c.
 #pragma once
+#include <type_traits>
 #include <cooperative_groups.h>
 #include "hg_device.cuh"
 
@@ -134,16 +135,20 @@ __global__ void k_grad_pd(Geo g, const double* __restrict__ u, const double* __r
 template <int DIM>
 __global__ void k_pre(Geo g, CP3 force, const double* __restrict__ pprev, P3 fcr, P3 gp) {
   CELL_LOOP_PROLOG(g)
+  auto body = [&](auto int_) {   // int_: interior cell, no boundary / excluded-cell tests (same arithmetic)
+    constexpr bool INT = decltype(int_)::value;
 #pragma unroll
-  for (int d = 0; d < DIM; ++d) {
-    double sum = 0.;
-    double fm = face_value<DIM, K_NEUMANN0>(g, force.p[d], d, i, j, k, 0);
-    double fp = face_value<DIM, K_NEUMANN0>(g, force.p[d], d, i + (d == 0), j + (d == 1), k + (d == 2), 0);
-    sum += (g.area[d] * fm) * (0.5 * g.h[d]);
-    sum += (g.area[d] * fp) * (0.5 * g.h[d]);
-    fcr.p[d][c] = sum / g.vol;
-    gp.p[d][c] = cell_grad<DIM, K_EXTRAP>(g, pprev, d, i, j, k, 0);
-  }
+    for (int d = 0; d < DIM; ++d) {
+      double sum = 0.;
+      double fm = face_value<DIM, K_NEUMANN0, INT>(g, force.p[d], d, i, j, k, 0);
+      double fp = face_value<DIM, K_NEUMANN0, INT>(g, force.p[d], d, i + (d == 0), j + (d == 1), k + (d == 2), 0);
+      sum += (g.area[d] * fm) * (0.5 * g.h[d]);
+      sum += (g.area[d] * fp) * (0.5 * g.h[d]);
+      fcr.p[d][c] = sum / g.vol;
+      gp.p[d][c] = cell_grad<DIM, K_EXTRAP, INT>(g, pprev, d, i, j, k, 0);
+    }
+  };
+  if (cell_interior<DIM>(g, i, j, k, 1)) body(std::true_type{}); else body(std::false_type{});
 }
 
 // K_velgrad: G[n*DIM+d] = d-component of Gradient(Interpolate(u_n, wall velocity)) -- used by the
@@ -151,10 +156,14 @@ __global__ void k_pre(Geo g, CP3 force, const double* __restrict__ pprev, P3 fcr
 template <int DIM>
 __global__ void k_velgrad(Geo g, CP3 u, P9 G) {
   CELL_LOOP_PROLOG(g)
+  auto body = [&](auto int_) {
+    constexpr bool INT = decltype(int_)::value;
 #pragma unroll
-  for (int n = 0; n < DIM; ++n)
+    for (int n = 0; n < DIM; ++n)
 #pragma unroll
-    for (int d = 0; d < DIM; ++d) G.p[n * DIM + d][c] = cell_grad<DIM, K_VEL>(g, u.p[n], d, i, j, k, n);
+      for (int d = 0; d < DIM; ++d) G.p[n * DIM + d][c] = cell_grad<DIM, K_VEL, INT>(g, u.p[n], d, i, j, k, n);
+  };
+  if (cell_interior<DIM>(g, i, j, k, 1)) body(std::true_type{}); else body(std::false_type{});
 }
 
 struct P9c { const double* p[9]; };
@@ -165,22 +174,26 @@ template <int DIM>
 __global__ void k_source(Geo g, P9c G, const double* __restrict__ mu, CP3 gp, CP3 fcr, CP3 stf, int use_stf, P3 fs) {
   CELL_LOOP_PROLOG(g)
   double acc[3] = {0., 0., 0.};
+  auto body = [&](auto int_) {
+  constexpr bool INT = decltype(int_)::value;
 #pragma unroll
   for (int n = 0; n < DIM; ++n) {
     int mi = i, mj = j, mk = k;
     int pi = i + (n == 0), pj = j + (n == 1), pk = k + (n == 2);
-    double mum = face_value<DIM, K_NEUMANN0>(g, mu, n, mi, mj, mk, 0);
-    double mup = face_value<DIM, K_NEUMANN0>(g, mu, n, pi, pj, pk, 0);
+    double mum = face_value<DIM, K_NEUMANN0, INT>(g, mu, n, mi, mj, mk, 0);
+    double mup = face_value<DIM, K_NEUMANN0, INT>(g, mu, n, pi, pj, pk, 0);
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
-      double gm = face_value<DIM, K_NEUMANN0>(g, G.p[n * DIM + d], n, mi, mj, mk, 0);
-      double gq = face_value<DIM, K_NEUMANN0>(g, G.p[n * DIM + d], n, pi, pj, pk, 0);
+      double gm = face_value<DIM, K_NEUMANN0, INT>(g, G.p[n * DIM + d], n, mi, mj, mk, 0);
+      double gq = face_value<DIM, K_NEUMANN0, INT>(g, G.p[n * DIM + d], n, pi, pj, pk, 0);
       double sum = 0.;
       sum += gm * (mum * (g.area[n] * -1.));
       sum += gq * (mup * (g.area[n] * 1.));
       acc[d] += sum / g.vol;
     }
   }
+  };
+  if (cell_interior<DIM>(g, i, j, k, 1)) body(std::true_type{}); else body(std::false_type{});
 #pragma unroll
   for (int d = 0; d < DIM; ++d) {
     double st = use_stf ? stf.p[d][c] : 0.;
@@ -221,6 +234,8 @@ __global__ void k_assemble(Geo g, AsmArgs a) {
     if (a.coeffsum) { double s = 0.; for (int n = 0; n < NCOMP; ++n) s += 1.; a.coeffsum[c] = s / a.coeffsum_div; }
     return;
   }
+  {
+  constexpr bool INT = false;   // an interior instantiation (face_info<DIM, true>) was measured slower here (register pressure)
   const int tmap[6] = {CXM, CXP, CYM, CYP, CZM, CZP};
   const long long off[7] = {-g.sz, -g.sy, -1, 0, 1, g.sy, g.sz};
   double cdiag = 0., ddiag = 0.;
@@ -235,7 +250,7 @@ __global__ void k_assemble(Geo g, AsmArgs a) {
     const int d = q >> 1, o = q & 1;
     const double sgn = o ? 1. : -1.;
     const int fi = i + (d == 0 ? o : 0), fj = j + (d == 1 ? o : 0), fk = k + (d == 2 ? o : 0);
-    FaceInfo f = face_info<DIM>(g, d, fi, fj, fk);
+    FaceInfo f = face_info<DIM, INT>(g, d, fi, fj, fk);
     if (f.type == FT_EXCL) continue;
     const double Ff = a.F[fidx(g, d, fi, fj, fk)];
     if (f.type == FT_INNER) {
@@ -328,6 +343,7 @@ __global__ void k_assemble(Geo g, AsmArgs a) {
   }
 #pragma unroll
   for (int t = 0; t < 7; ++t) if (DIM > 2 || (t != CZM && t != CZP)) a.A[t][cs] = coef[t];
+  }
 }
 
 // u_curr = u_prev + corr (conv_diff.hpp:246-248); corr is in the sheared layout
@@ -496,11 +512,11 @@ __global__ void k_pcorr(Geo g, const double* __restrict__ PP, const double* __re
 // K_correct: velocity correction u += -grad p' / d_c (fluid.hpp:1040-1050) and the divergence-free
 // fluxes F = F* + c_f (p'_m - p'_p) (fluid.hpp:1053-1056)
 struct CorrArgs { const double* pc; const double* dc; const double* Fs; double* u[3]; double* F; };
-template <int DIM>
+template <int DIM, bool INT = false>
 DV double fcorr_face(const Geo& g, const CorrArgs& a, int d, int fi, int fj, int fk) {
   const long long fx = fidx(g, d, fi, fj, fk);
   double r = a.Fs[fx];
-  FaceInfo f = face_info<DIM>(g, d, fi, fj, fk);
+  FaceInfo f = face_info<DIM, INT>(g, d, fi, fj, fk);
   if (f.type == FT_INNER) {
     const double cf = face_coeff<DIM>(g, a.dc, d, f);
     r += a.pc[f.cm] * cf;
@@ -511,17 +527,21 @@ DV double fcorr_face(const Geo& g, const CorrArgs& a, int d, int fi, int fj, int
 template <int DIM>
 __global__ void k_correct(Geo g, CorrArgs a) {
   CELL_LOOP_PROLOG(g)
+  auto body = [&](auto int_) {
+    constexpr bool INT = decltype(int_)::value;
 #pragma unroll
-  for (int d = 0; d < DIM; ++d) {
-    const double gpc = cell_grad<DIM, K_EXTRAP>(g, a.pc, d, i, j, k, 0);
-    a.u[d][c] += gpc / (-a.dc[c]);
-    a.F[fidx(g, d, i, j, k)] = fcorr_face<DIM>(g, a, d, i, j, k);
-    const int x = d == 0 ? i : (d == 1 ? j : k);
-    if (x == g.n[d] - 1) {
-      const int fi = i + (d == 0), fj = j + (d == 1), fk = k + (d == 2);
-      a.F[fidx(g, d, fi, fj, fk)] = fcorr_face<DIM>(g, a, d, fi, fj, fk);
+    for (int d = 0; d < DIM; ++d) {
+      const double gpc = cell_grad<DIM, K_EXTRAP, INT>(g, a.pc, d, i, j, k, 0);
+      a.u[d][c] += gpc / (-a.dc[c]);
+      a.F[fidx(g, d, i, j, k)] = fcorr_face<DIM, INT>(g, a, d, i, j, k);
+      const int x = d == 0 ? i : (d == 1 ? j : k);
+      if (!INT && x == g.n[d] - 1) {
+        const int fi = i + (d == 0), fj = j + (d == 1), fk = k + (d == 2);
+        a.F[fidx(g, d, fi, fj, fk)] = fcorr_face<DIM>(g, a, d, fi, fj, fk);
+      }
     }
-  }
+  };
+  body(std::false_type{});   // the interior instantiation was measured slightly slower for this kernel
 }
 
 // K_resid: CalcDiff of vector fields, max_c ||a - b||_2 (solver.hpp:804-813)
