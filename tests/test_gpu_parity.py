@@ -186,6 +186,33 @@ def test_gs_tiled_equals_hyperplane_kernel(case, monkeypatch):
         assert np.array_equal(fa[n], fb[n]), n
 
 
+@pytest.mark.parametrize("case", ["rt3d_40x36x20", "dam3d_64x20x20", "rt3d_9x5x4", "thermal3d_33x18x12", "rt3d_70x40x9"])
+def test_lu_tiled_equals_hyperplane_kernel(case, monkeypatch):
+    """The column-box dataflow of the lu solver (hg_lu_tiled.cuh) and the hyperplane kernel with a grid barrier per plane
+    (hg_solvers.cuh) are two schedules of the same forward + backward sweep (linear.hpp:533-566): bitwise equal."""
+    from hydro_b200.capi import Hydro
+    p = {"rt3d_40x36x20": cases.rt3d(8, Nx=40, Ny=36, Nz=20, lu_relaxed_num_iters_limit=9),
+         "dam3d_64x20x20": cases.broken_dam_3d(64, 20, 20, lu_relaxed_num_iters_limit=12),
+         "rt3d_9x5x4": cases.rt3d(8, Nx=9, Ny=5, Nz=4, lu_relaxed_num_iters_limit=11),
+         "thermal3d_33x18x12": cases.rt3d(8, Nx=33, Ny=18, Nz=12, lu_relaxed_num_iters_limit=7, heat_enable=1,
+                                          heat_box_lb=(-1., -1., -1.), heat_box_rt=(2., 0.01, 2.), heat_box_temperature=1.),
+         "rt3d_70x40x9": cases.rt3d(8, Nx=70, Ny=40, Nz=9, lu_relaxed_num_iters_limit=5)}[case]
+    names = ["VELOCITY_X", "VELOCITY_Y", "VELOCITY_Z", "PRESSURE", "VOLUME_FLUX", "PARTIAL_DENSITY_1"]
+    if p.get("heat_enable"):
+        names.append("TEMPERATURE")
+    res = []
+    for kern in ("tiled", "hyperplane"):
+        monkeypatch.setenv("HYDRO_LU_KERNEL", kern)
+        h = Hydro(p)
+        st = [h.step() for _ in range(2)][-1]
+        res.append((st, {n: h.get(n) for n in names}))
+        h.close()
+    (sa, fa), (sb, fb) = res
+    assert sa.convergence_indicator == sb.convergence_indicator
+    for n in fa:
+        assert np.array_equal(fa[n], fb[n]), n
+
+
 def test_gpu_tvd_split_and_surface_tension():
     run_both(cases.broken_dam_2d(40, 24, tvd_split=1, sigma=0.07, lu_relaxed_num_iters_limit=40), 2, tol=1e-11)
 
