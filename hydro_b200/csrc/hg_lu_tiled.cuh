@@ -21,7 +21,7 @@
 #include "hg_device.cuh"
 
 #ifndef LT_M_N
-#define LT_M_N 8
+#define LT_M_N 4
 #endif
 constexpr int LT_TX = 32, LT_TY = 16, LT_M = LT_M_N, LT_PF = 4;   // LT_M % LT_PF == 0: operand slots are compile-time
 constexpr int LT_THREADS = LT_TX * LT_TY;
