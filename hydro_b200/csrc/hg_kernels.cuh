@@ -133,7 +133,7 @@ __global__ void k_grad_pd(Geo g, const double* __restrict__ u, const double* __r
 // K_pre: restored external force (CalcExtForce, fluid.hpp:602-631) and pressure gradient
 // Gradient(Interpolate(p_prev, extrapolation)) (fluid.hpp:827-829)
 template <int DIM>
-__global__ void k_pre(Geo g, CP3 force, const double* __restrict__ pprev, P3 fcr, P3 gp) {
+__global__ void __launch_bounds__(256, 8) k_pre(Geo g, CP3 force, const double* __restrict__ pprev, P3 fcr, P3 gp) {
   CELL_LOOP_PROLOG(g)
   auto body = [&](auto int_) {   // int_: interior cell, no boundary / excluded-cell tests (same arithmetic)
     constexpr bool INT = decltype(int_)::value;
@@ -171,7 +171,7 @@ struct P9c { const double* p[9]; };
 // K_source: momentum source = explicit viscous term + (-grad p + restored force + surface tension)
 // (fluid.hpp:835-870)
 template <int DIM>
-__global__ void k_source(Geo g, P9c G, const double* __restrict__ mu, CP3 gp, CP3 fcr, CP3 stf, int use_stf, P3 fs) {
+__global__ void __launch_bounds__(256, 8) k_source(Geo g, P9c G, const double* __restrict__ mu, CP3 gp, CP3 fcr, CP3 stf, int use_stf, P3 fs) {
   CELL_LOOP_PROLOG(g)
   double acc[3] = {0., 0., 0.};
   auto body = [&](auto int_) {
@@ -224,7 +224,7 @@ struct AsmArgs {
   int out_sheared;         // 1: A/R are written in the sheared layout directly; 0: natural (k_shear3 follows)
 };
 template <int DIM, int KIND, int NCOMP>
-__global__ void k_assemble(Geo g, AsmArgs a) {
+__global__ void __launch_bounds__(256, 5) k_assemble(Geo g, AsmArgs a) {
   CELL_LOOP_PROLOG(g)
   const long long cs = a.out_sheared ? shidx(g, i, j, k) : c;
   if (cell_excl(g, i, j, k)) {   // conv_diff.hpp:222-226
@@ -381,7 +381,7 @@ DV double fstar_face(const Geo& g, const FstarArgs& a, int d, int fi, int fj, in
   return ffu * A - mv;
 }
 template <int DIM>
-__global__ void k_fstar(Geo g, FstarArgs a) {
+__global__ void __launch_bounds__(256, 6) k_fstar(Geo g, FstarArgs a) {
   CELL_LOOP_PROLOG(g)
   (void)c;
 #pragma unroll
@@ -406,7 +406,7 @@ DV double face_coeff(const Geo& g, const double* __restrict__ dc, int d, const F
 // K_prhs: constants of the pressure-correction rows (fluid.hpp:972-1014) and the diagonal field in
 // the sheared layout; the sweep kernels regenerate the off-diagonals A/(h d_f) from it.
 template <int DIM>
-__global__ void k_prhs(Geo g, const double* __restrict__ Fs, const double* __restrict__ dc, int out_sheared,
+__global__ void __launch_bounds__(256, 6) k_prhs(Geo g, const double* __restrict__ Fs, const double* __restrict__ dc, int out_sheared,
                        double* __restrict__ RP, double* __restrict__ CX, double* __restrict__ CY, double* __restrict__ CZ,
                        double* __restrict__ DG = nullptr) {
   CELL_LOOP_PROLOG(g)
@@ -525,7 +525,7 @@ DV double fcorr_face(const Geo& g, const CorrArgs& a, int d, int fi, int fj, int
   return r;
 }
 template <int DIM>
-__global__ void k_correct(Geo g, CorrArgs a) {
+__global__ void __launch_bounds__(256, 6) k_correct(Geo g, CorrArgs a) {
   CELL_LOOP_PROLOG(g)
   auto body = [&](auto int_) {
     constexpr bool INT = decltype(int_)::value;
@@ -619,7 +619,7 @@ DV double adv_face_value(const Geo& g, const double* __restrict__ u, const doubl
   return 0.5 * (uP + uE);
 }
 template <int DIM>
-__global__ void k_advect(Geo g, const double* __restrict__ u, const double* __restrict__ pdinit,
+__global__ void __launch_bounds__(256, 8) k_advect(Geo g, const double* __restrict__ u, const double* __restrict__ pdinit,
                          const double* __restrict__ F, double dt, int num_stages, int stage, double* __restrict__ out) {
   CELL_LOOP_PROLOG(g)
   double fsum = 0.;
@@ -638,7 +638,7 @@ __global__ void k_advect(Geo g, const double* __restrict__ u, const double* __re
 // out[ph*12 + {0 volume, 1..3 centre sums, 4..6 velocity sums}] (atomicAdd), out[ph*12+7] pd_min, +8 pd_max
 struct StatArgs { int np; const double* vf[3]; const double* pd[3]; const double* u[3]; double* out; };
 template <int DIM>
-__global__ void k_stat(Geo g, StatArgs a) {
+__global__ void __launch_bounds__(256, 6) k_stat(Geo g, StatArgs a) {
   long long c_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long nc_ = (long long)g.n[0] * g.n[1] * g.n[2];
   const bool ok = c_ < nc_;
