@@ -784,12 +784,14 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
   tpush(s, "fluid.5.pressure-system");
   if (s->dim == 3) {
     DIMSEL(s, k_prhs, gb, 256, s->geo, s->Fs, s->dc, 0, s->An[0], s->An[1], s->An[2], s->An[3], s->gs_tiled ? s->An[4] : nullptr);
-    double* outs[5] = {s->RP, s->D, s->CYs, s->CZs, s->DGs};
-    shear_arrays(s, s->An, outs, s->gs_tiled ? 5 : 4);
     if (s->gs_tiled) {
-      GtPackArgs pa; pa.RP = s->RP; pa.DG = s->DGs; pa.CX = s->D; pa.CY = s->CYs; pa.CZ = s->CZs; pa.CO = s->CO;
-      k_gt_pack<<<dim3((s->n[0] + 31) / 32, (s->n[1] + 7) / 8, s->geo.np), 256, 0, s->st>>>(s->geo, pa);
+      // natural -> packed rows of k_gs_tiled in one pass (transpose + packing)
+      GtPackArgs pa; pa.RP = s->An[0]; pa.CX = s->An[1]; pa.CY = s->An[2]; pa.CZ = s->An[3]; pa.DG = s->An[4]; pa.CO = s->CO;
+      k_gt_shear_pack<<<dim3((s->n[0] + 31) / 32, s->n[1], (s->n[2] + 31) / 32), 256, 0, s->st>>>(s->geo, pa);
       ++s->launches;
+    } else {
+      double* outs[4] = {s->RP, s->D, s->CYs, s->CZs};
+      shear_arrays(s, s->An, outs, 4);
     }
     if (s->geo.zlo > 0) { k_cz_halo<3><<<nblk(s->nxy), 256, 0, s->st>>>(s->geo, s->dc, s->CZs); ++s->launches; }
   } else {
