@@ -23,7 +23,10 @@
 #ifndef LT_M_N
 #define LT_M_N 4
 #endif
-constexpr int LT_TX = 32, LT_TY = 16, LT_M = LT_M_N, LT_PF = 4;   // LT_M % LT_PF == 0: operand slots are compile-time
+#ifndef LT_TY_N
+#define LT_TY_N 8
+#endif
+constexpr int LT_TX = 32, LT_TY = LT_TY_N, LT_M = LT_M_N, LT_PF = 4;   // LT_M % LT_PF == 0: operand slots are compile-time
 constexpr int LT_THREADS = LT_TX * LT_TY;
 constexpr int LT_FW = LT_TX + 1, LT_FH = LT_TY + 1, LT_FRAME = LT_FW * LT_FH;   // frame: halo column / row at index 0
 constexpr int LT_HALO = LT_TX + LT_TY;            // halo entries per frame: column 0 (rows 1..TY), row 0 (columns 1..TX)

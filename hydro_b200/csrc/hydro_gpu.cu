@@ -559,7 +559,7 @@ static int solve_lu_tiled(hg_state* s, int ncomp) {
   a.ncomp = ncomp; a.boxes = s->lt_boxes; a.nboxes = s->lt_nboxes; a.nbi = s->lt_nbi; a.progress = s->lt_progress; a.ctl = s->lt_ctl;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (s->profile_on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s->st); }
-  const int grid = std::min(s->lt_nboxes, s->num_sms);
+  const int grid = std::min(s->lt_nboxes, s->num_sms * std::max(1, 512 / LT_THREADS));   // all boxes resident when they fit
   for (int dir = 0; dir < 2; ++dir) {
     CK(cudaMemsetAsync(s->lt_progress, 0, s->lt_nboxes * sizeof(int), s->st));
     CK(cudaMemsetAsync(s->lt_ctl, 0, sizeof(int), s->st));   // next-box counter; the abort flag [1] is sticky
