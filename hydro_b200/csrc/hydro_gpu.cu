@@ -477,7 +477,7 @@ static int gt_launch(hg_state* s, int sb, int se, double omega) {
   CK(cudaMemsetAsync(s->gt_ctl, 0, sizeof(int), s->st));   // next-task counter; the abort flag [1] is sticky
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (s->profile_on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s->st); }
-  const int grid = std::min(pl->ntasks, s->num_sms);
+  const int grid = std::min(pl->ntasks, s->num_sms * GT_CTAS_PER_SM);
   k_gs_tiled<<<grid, GT_BLOCK, GT_SMEM_BYTES, s->st>>>(s->geo, a, s->tmco);
   CK(cudaGetLastError());
   if (e0) { cudaEventRecord(e1, s->st); s->prof_ev[0].push_back({e0, e1}); }
