@@ -19,6 +19,7 @@
 // The arithmetic (term order z, y, x; one division per component) is that of k_lu_persistent: bit-identical.
 #pragma once
 #include "hg_device.cuh"
+#include "hg_slab.cuh"
 
 #ifndef LT_M_N
 #define LT_M_N 4
@@ -41,6 +42,8 @@ struct LtArgs {
   int nboxes, nbi;      // boxes, boxes along i
   int* progress;        // [nboxes] completed steps + LT_PBIAS, indexed J' * nbi + I'; zeroed before the launch
   int* ctl;             // [0] next box, [1] abort flag
+  SlabLink link;        // z-slab decomposition: tagged interface planes of the neighbouring slabs (hg_slab.cuh); component n at + n link_stride
+  long long link_stride;
 };
 
 DV int lt_ld_acquire(const int* p) {
@@ -52,8 +55,11 @@ DV void lt_st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
-// DIR = 0: forward sweep, DIR = 1: backward sweep
-template <int DIR>
+// DIR = 0: forward sweep, DIR = 1: backward sweep.  LINK: the mesh is one z-slab of a decomposed run -- the first cell of
+// a column takes its z-neighbour from the slab the sweep comes from (a value tagged with the solve, written by that
+// slab's thread when it finished the column: the data is its own flag), the last cell hands its value on.  The slabs
+// run the same kernel concurrently; a slab's wavefront simply starts when the first columns of its neighbour are done.
+template <int DIR, bool LINK = false>
 __global__ void __launch_bounds__(LT_THREADS, 1) k_lu_tiled(Geo g, LtArgs a) {
   __shared__ double fr[2][3][LT_FRAME];            // values of the last two steps
   __shared__ double stage[LT_M][3][LT_HALO];       // halo values of the LT_M steps of a macro step
@@ -157,7 +163,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_lu_tiled(Geo g, LtArgs a) {
         const int kp = S - ip - jp;
         const bool v = col && kp >= 0 && kp < nz;
         const int k = DIR ? nz - 1 - kp : kp;
-        const bool hz = DIR ? k + 1 < nz : k > 0;
+        const bool zin = LINK && (DIR ? a.link.has_hi : a.link.has_lo) && kp == 0;      // z-neighbour in the other slab
+        const bool hz = (DIR ? k + 1 < nz : k > 0) || zin;
         const int slot = st % LT_PF;
         const double cz = pz[slot], cy = py[slot], cx = px[slot], dg = pd[slot];
         const HgDiv ddg = hg_div_prepare(dg);   // one reciprocal for the components
@@ -177,6 +184,11 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_lu_tiled(Geo g, LtArgs a) {
         __syncthreads();
         double* const fprev = f0 + (par ^ 1) * 3 * LT_FRAME;
         double* const fcur = f0 + par * 3 * LT_FRAME;
+        if (LINK && v && zin) {
+          const uint4* const from = (DIR ? a.link.from_hi : a.link.from_lo) + (long long)j * nx + i;
+#pragma unroll
+          for (int n = 0; n < 3; ++n) if (n < a.ncomp) xz[n] = ll_wait(from + n * a.link_stride, a.link.tag0 + (DIR ? 2u : 1u), a.link.err);
+        }
 #pragma unroll
         for (int n = 0; n < 3; ++n) {
           double xv = 0.;
@@ -188,6 +200,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_lu_tiled(Geo g, LtArgs a) {
             if (hx) sum += cx * vx;
             xv = DIR ? rr[n] - hg_div(sum, ddg) : hg_div(-rr[n] - sum, ddg);
             if (v) a.X[n][cs] = xv; else xv = 0.;
+            if (LINK && v && kp == nz - 1 && (DIR ? a.link.has_lo : a.link.has_hi))
+              ll_store((DIR ? a.link.to_lo : a.link.to_hi) + n * a.link_stride + (long long)j * nx + i, xv, a.link.tag0 + (DIR ? 2u : 1u));
           }
           fcur[n * LT_FRAME] = xv;
           xz[n] = xv;
