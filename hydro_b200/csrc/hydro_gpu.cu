@@ -477,8 +477,11 @@ static int gt_launch(hg_state* s, int sb, int se, double omega) {
   CK(cudaMemsetAsync(s->gt_ctl, 0, sizeof(int), s->st));   // next-task counter; the abort flag [1] is sticky
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (s->profile_on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s->st); }
-  const int grid = std::min(pl->ntasks, s->num_sms * GT_CTAS_PER_SM);
-  k_gs_tiled<<<grid, GT_BLOCK, GT_SMEM_BYTES, s->st>>>(s->geo, a, s->tmco);
+  int grid = std::min(pl->ntasks, s->num_sms * GT_CTAS_PER_SM);
+  if (s->cfg.solver_ctas > 0) grid = std::min(grid, s->cfg.solver_ctas);   // ranks sharing a device (tests)
+  a.link = slab_link(s, 0);
+  if (s->world > 1) k_gs_tiled<true><<<grid, GT_BLOCK, GT_SMEM_BYTES, s->st>>>(s->geo, a, s->tmco);
+  else k_gs_tiled<false><<<grid, GT_BLOCK, GT_SMEM_BYTES, s->st>>>(s->geo, a, s->tmco);
   CK(cudaGetLastError());
   if (e0) { cudaEventRecord(e1, s->st); s->prof_ev[0].push_back({e0, e1}); }
   ++s->launches;
@@ -794,7 +797,7 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
     DIMSEL(s, k_prhs, gb, 256, s->geo, s->Fs, s->dc, 0, s->An[0], s->An[1], s->An[2], s->An[3], s->gs_tiled ? s->An[4] : nullptr);
     if (s->gs_tiled) {
       // natural -> packed rows of k_gs_tiled in one pass (transpose + packing)
-      GtPackArgs pa; pa.RP = s->An[0]; pa.CX = s->An[1]; pa.CY = s->An[2]; pa.CZ = s->An[3]; pa.DG = s->An[4]; pa.CO = s->CO;
+      GtPackArgs pa; pa.RP = s->An[0]; pa.CX = s->An[1]; pa.CY = s->An[2]; pa.CZ = s->An[3]; pa.DG = s->An[4]; pa.CO = s->CO; pa.dc = s->dc;
       k_gt_shear_pack<<<dim3((s->n[0] + 31) / 32, s->n[1], (s->n[2] + 31) / 32), 256, 0, s->st>>>(s->geo, pa);
       ++s->launches;
     } else {
@@ -1162,7 +1165,7 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     for (int n = 0; n < dim; ++n) { T.R[n] = take(s->nsh); T.X[n] = take(s->nsh); }
     // the tile sweeps read a few hyperplanes beyond both ends of the solution and of the x+/y+ coefficient arrays:
     // GT_PAD zero hyperplanes around them (never written)
-    const long long padn = (dim == 3 && s->world == 1) ? (long long)GT_PAD * s->nxy : 0;
+    const long long padn = dim == 3 ? (long long)GT_PAD * s->nxy : 0;
     auto take_padded = [&](long long n) -> double* { double* q = take(n + 2 * padn); return q ? q + padn : nullptr; };
     T.D = take_padded(s->nsh); T.CYs = take_padded(s->nsh); T.CZs = take(dim > 2 ? s->nsh : 1); T.RP = take(s->nsh);
     T.PP = take_padded(s->nsh); T.PPsave = take(s->nsh);
@@ -1170,7 +1173,8 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     // pressure sweeps: time-skewed tiles in 3-D on one GPU (HYDRO_GS_KERNEL=hyperplane keeps the pipelined
     // hyperplane kernel, which is also what 2-D and the slab-decomposed runs use)
     { const char* e = getenv("HYDRO_GS_KERNEL");
-      T.gs_tiled = dim == 3 && s->world == 1 && cfg->linear_solver_pressure == HG_LS_GAUSS_SEIDEL && !(e && !strcmp(e, "hyperplane")) &&
+      const char* es = getenv("HYDRO_GS_SLAB_KERNEL");
+      T.gs_tiled = dim == 3 && !(s->world > 1 && es && !strcmp(es, "hyperplane")) && cfg->linear_solver_pressure == HG_LS_GAUSS_SEIDEL && !(e && !strcmp(e, "hyperplane")) &&
                    8LL * (GT_PAD + 2) * s->nxy < (1LL << 31);   // 32-bit byte offsets inside k_gs_tiled
     }
     if (T.gs_tiled) {
@@ -1222,7 +1226,8 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail_create(s, HG_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r)); }
-    if (cudaFuncSetAttribute(k_gs_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_gs_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_gs_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES) != cudaSuccess)
       return fail_create(s, HG_ERR_CUDA, "k_gs_tiled: shared memory request rejected");
   }
   { const char* e = getenv("HYDRO_LU_KERNEL");

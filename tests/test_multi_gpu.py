@@ -31,9 +31,14 @@ def devices_for(world):
     return (list(range(world)), 0) if n >= world else ([0] * world, 148 // world - 2)
 
 
+@pytest.mark.parametrize("kernel", ["hyperplane", "tiled"])
 @pytest.mark.parametrize("case,world", [("rt3d_16", 2), ("rt3d_20x12x17", 3), ("dam3d_32x10x12", 2), ("rt3d_tol", 2)])
-def test_slabs_equal_single_gpu(case, world, monkeypatch):
-    monkeypatch.setenv("HYDRO_GS_KERNEL", "hyperplane")   # same sweep kernel on both sides (bitwise equal anyway)
+def test_slabs_equal_single_gpu(case, world, kernel, monkeypatch):
+    # hyperplane: the neighbour-linked hyperplane kernels on both sides; tiled: the box-dataflow kernels (k_gs_tiled,
+    # k_lu_tiled) with tagged interface values between the slabs -- all bitwise equal to the single-GPU run
+    if kernel == "hyperplane":
+        monkeypatch.setenv("HYDRO_GS_KERNEL", "hyperplane")
+        monkeypatch.setenv("HYDRO_LU_KERNEL", "hyperplane")
     p = {"rt3d_16": cases.rt3d(16),
          "rt3d_20x12x17": cases.rt3d(8, Nx=20, Ny=12, Nz=17, lu_relaxed_num_iters_limit=30),
          "dam3d_32x10x12": cases.broken_dam_3d(32, 10, 12, lu_relaxed_num_iters_limit=40),
