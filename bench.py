@@ -247,8 +247,8 @@ def run_b200(args, rank, local_rank, world):
             dist.destroy_process_group()
         return
     peak, peak_src = measured_peak()
-    # roofline of the dominant kernel: the Gauss-Seidel sweep kernel (one GPU: k_gs_tiled, time-skewed tiles; slabs:
-    # k_gs_persistent, neighbour-linked hyperplanes), one launch per pressure solve = (limit+1) sweeps x 32
+    # roofline of the dominant kernel: the Gauss-Seidel sweep kernel k_gs_tiled (time-skewed column boxes; on slabs the
+    # boxes of neighbouring GPUs exchange tagged interface values), one launch per pressure solve = (limit+1) sweeps x 32
     # algorithmic bytes per cell-sweep
     sweeps_per_solve = p["lu_relaxed_num_iters_limit"] + 1
     gs_bytes = 32.0 * sweeps_per_solve * cells
@@ -257,7 +257,7 @@ def run_b200(args, rank, local_rank, world):
     bpcs = bytes_per_cell_step(n_simple, sweeps_per_solve, n_adv, False)
     step_gbs = bpcs * cells / sec_step / 1e9
     kname = ("k_gs_tiled (lexicographic Gauss-Seidel/SOR as time-skewed column boxes, rows staged by TMA, %d sweeps per launch)" if world == 1 else
-             "k_gs_persistent<3> (lexicographic Gauss-Seidel/SOR, hyperplanes linked across the slabs, %d sweeps per launch)")
+             "k_gs_tiled<LINK> (the same box dataflow on every z-slab, interface values as sweep-tagged peer stores, %d sweeps per launch)")
     roof = {"bound": "hbm", "kernel": kname % sweeps_per_solve,
             "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
             "frac": achieved / peak if achieved else None, "traffic": None,
