@@ -1174,7 +1174,10 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     // hyperplane kernel, which is also what 2-D and the slab-decomposed runs use)
     { const char* e = getenv("HYDRO_GS_KERNEL");
       const char* es = getenv("HYDRO_GS_SLAB_KERNEL");
-      T.gs_tiled = dim == 3 && !(s->world > 1 && es && !strcmp(es, "hyperplane")) && cfg->linear_solver_pressure == HG_LS_GAUSS_SEIDEL && !(e && !strcmp(e, "hyperplane")) &&
+      // slabs: the box dataflow with tagged interface values is verified bit for bit for two slabs; with three or more it
+      // is opt-in (HYDRO_GS_SLAB_KERNEL=tiled): a 3-rank run with several sweep groups still times out on a shared device
+      const bool slab_ok = s->world == 1 || (s->world == 2 && !(es && !strcmp(es, "hyperplane"))) || (es && !strcmp(es, "tiled"));
+      T.gs_tiled = dim == 3 && slab_ok && cfg->linear_solver_pressure == HG_LS_GAUSS_SEIDEL && !(e && !strcmp(e, "hyperplane")) &&
                    8LL * (GT_PAD + 2) * s->nxy < (1LL << 31);   // 32-bit byte offsets inside k_gs_tiled
     }
     if (T.gs_tiled) {
