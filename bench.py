@@ -30,8 +30,16 @@ METRIC = "cell-updates/s per timestep incl. pressure solve"
 UNIT = "cell-updates/s"
 
 
-def workload_params(n):
+def workload_params(n, workload="rt", as_configured=False):
+    """rt: W4 Rayleigh-Taylor 3-D n^3, fixed work (3 SIMPLE x 101 sweeps) or as configured (<= 20 SIMPLE iterations, tol 1e-4,
+    Gauss-Seidel <= 1000 sweeps, tol 1e-5: SURVEY 8d).  dam: W5 examples/broken_dam_3d at n^3 (domain 3.2 x 1 x 1, obstacle
+    box, 5 SIMPLE iterations, 10 advection sub-steps) with the sweeps fixed at 101 per solve."""
     import cases
+    if workload == "dam":
+        return cases.broken_dam_3d(n, n, n, lu_relaxed_num_iters_limit=100, lu_relaxed_tolerance=0.0, convergence_tolerance=0.0)
+    if as_configured:
+        return cases.rt3d(n, fixed_work=False, lu_relaxed_num_iters_limit=1000, lu_relaxed_tolerance=1e-5,
+                          num_iterations_limit=20, convergence_tolerance=1e-4)
     return cases.rt3d(n, fixed_work=True)
 
 
@@ -97,12 +105,22 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_reference_run(n, steps, warmup):
+def cpu_model():
+    try:
+        for l in open("/proc/cpuinfo"):
+            if l.startswith("model name"):
+                return l.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def cpu_reference_run(n, steps, warmup, threads=None):
     """The reference's own CPU implementation on the box's host cores: returns (cell-updates/s, info)."""
     import refrun
     p = workload_params(n)
     cells = n ** 3
-    cores = os.cpu_count() or 1
+    cores = threads or os.cpu_count() or 1
     if os.access(refrun.REF_HYDRO, os.X_OK):
         t_all, timers, _ = refrun.run_reference_binary(p, steps + warmup, threads=cores)
         use = t_all[warmup:] if len(t_all) > warmup else t_all
@@ -134,6 +152,16 @@ def run_reference(args, rank, world):
     val, sec, info = cpu_reference_run(n, args.steps, max(args.warmup, 1))
     info["value"] = val
     info["unit"] = UNIT
+    info["cpu_model"] = cpu_model()
+    # OMP_NUM_THREADS 1 and all cores, 64^3 and 128^3 (bounded: 2 timed steps each)
+    extra = []
+    for (en, ethreads) in ((n, 1), (128, None)):
+        try:
+            v, sec2, inf2 = cpu_reference_run(en, 2, 1, threads=ethreads)
+            extra.append({"size": en, "cores": inf2["cores"], "value": v, "ms_per_step": sec2 * 1e3, "kind": inf2["kind"]})
+        except Exception as e:   # a report, never a gate
+            extra.append({"size": en, "error": str(e)[:160]})
+    info["extra"] = extra
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -143,6 +171,51 @@ def run_reference(args, rank, world):
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def slab_parity_check(dist, rank, world, local_rank, n=64, nsteps=2):
+    """One process per GPU, CUDA IPC, NVLink peer stores -- the path the scaling numbers are measured on -- against the
+    single-GPU run of the same case on rank 0: the gathered slab fields must be bit-identical."""
+    import numpy as np
+    import torch
+    import cases
+    from hydro_b200 import parallel
+    from hydro_b200.capi import Hydro
+    from hydro_b200.config import F, FACE_FIELDS
+    p = cases.rt3d(n, Nx=n, Ny=n - 16, Nz=n)
+    names = ["VELOCITY_X", "VELOCITY_Y", "VELOCITY_Z", "PRESSURE", "VOLUME_FLUX", "PARTIAL_DENSITY_1"]
+    h = Hydro(p, device=local_rank, world_size=world, rank=rank)
+    h.link_ipc(dist)
+    st = None
+    for _ in range(nsteps):
+        st = h.step()
+    parts = {}
+    for nm in names:
+        mine = torch.from_numpy(h.get(nm)).cuda()
+        sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([mine.numel()], dtype=torch.int64, device="cuda"))
+        mx = max(int(x.item()) for x in sizes)
+        buf = torch.zeros(mx, dtype=torch.float64, device="cuda")
+        buf[:mine.numel()] = mine
+        outs = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(outs, buf)
+        parts[nm] = [o[:int(sz.item())].cpu().numpy() for o, sz in zip(outs, sizes)]
+    h.close()
+    if rank != 0:
+        return None
+    one = Hydro(p, device=local_rank)
+    s1 = None
+    for _ in range(nsteps):
+        s1 = one.step()
+    bad = []
+    for nm in names:
+        whole = (parallel.join_faces(parts[nm], n, n - 16, n, world) if F[nm] in FACE_FIELDS else parallel.join_cells(parts[nm]))
+        if not np.array_equal(whole, one.get(nm)):
+            bad.append(nm)
+    if st.pressure_sweeps_total != s1.pressure_sweeps_total or st.convergence_indicator != s1.convergence_indicator:
+        bad.append("counts")
+    one.close()
+    return "bit-exact (%dx%dx%d, %d steps, %d slabs over IPC vs 1 GPU)" % (n, n - 16, n, nsteps, world) if not bad else "MISMATCH: " + ",".join(bad)
 
 
 def run_b200(args, rank, local_rank, world):
@@ -157,18 +230,28 @@ def run_b200(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     n = args.size
-    p = workload_params(n)
-    mesh = weak_mesh(n, world)
+    p = workload_params(n, args.workload)
+    strong = args.scaling == "strong"
+    parity = None
     if world > 1:
-        # weak scaling: n^3 cells per GPU, same cell size; z-slabs of a mesh that is kept as cubic as possible
-        # (the lexicographic sweeps are a wavefront over i+j+k: its length, nx+ny+nz, is the serial part)
-        fx, fy, fz = mesh[0] / n, mesh[1] / n, mesh[2] / n
-        p.update(Nx=mesh[0], Ny=mesh[1], Nz=mesh[2], B=(fx, fy, fz), B1=(fx, 0.5 * fy, fz))
+        parity = slab_parity_check(dist, rank, world, local_rank)
+        if strong:
+            # strong scaling: the n^3 mesh of the single-GPU run, cut into z-slabs
+            mesh = (n, n, n)
+        else:
+            # weak scaling: n^3 cells per GPU, same cell size; z-slabs of a mesh that is kept as cubic as possible
+            # (the lexicographic sweeps are a wavefront over i+j+k: its length, nx+ny+nz, is the serial part)
+            mesh = weak_mesh(n, world)
+            fx, fy, fz = mesh[0] / n, mesh[1] / n, mesh[2] / n
+            B, B1 = p["B"], p["B1"]
+            p.update(Nx=mesh[0], Ny=mesh[1], Nz=mesh[2], B=(B[0] * fx, B[1] * fy, B[2] * fz), B1=(B1[0] * fx, B1[1] * fy, B1[2] * fz))
         h = Hydro(p, device=local_rank, world_size=world, rank=rank)
         h.link_ipc(dist)
     else:
+        mesh = (n, n, n)
         h = Hydro(p, device=local_rank)
     cells = h.nc
+    total_cells = mesh[0] * mesh[1] * mesh[2]
     K, W = args.steps, max(args.warmup, 3)
 
     def barrier():
@@ -177,9 +260,17 @@ def run_b200(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    launches0 = None
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for _ in range(W):
         st = h.step()
+    if os.environ.get("HYDRO_GT_CLOCK"):
+        h.profile_read_clocks()
     n_simple, sweeps, n_adv = st.simple_iterations, st.pressure_sweeps_total, st.advection_substeps
     # ---- device-resident timing
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -195,18 +286,18 @@ def run_b200(args, rank, local_rank, world):
         st = h.step()
     h.event_record(1)
     barrier()
-    ms = h.event_elapsed_ms(0, 1)
+    ms = allmax(h.event_elapsed_ms(0, 1))
     launches = h.launch_count() - launches0
     gs_n, gs_ms = h.profile_read(0)
     lu_n, lu_ms = h.profile_read(1)
     h.profile_enable(False)
+    if os.environ.get("HYDRO_GT_CLOCK") and rank == 0:
+        # instrumented build (-DGT_CLOCK): cycles per warp role, summed over warps: producer store+publish / poll+load /
+        # barrier wait; sweep warps barrier wait / step
+        print("gt_clocks", h.profile_read_clocks()[:8], "launches", gs_n, file=sys.stderr)
     clocks = sampler.stop() if sampler else None
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     sec_step = ms * 1e-3 / K
-    value = world * cells / sec_step
+    value = total_cells / sec_step
 
     # ---- end to end through the C ABI with pinned host buffers (SURVEY 8b secondary boundary: the
     # fields FluidSimple reads from caller memory every iteration, hydro2d.hpp:449-463, are uploaded each step;
@@ -217,7 +308,7 @@ def run_b200(args, rank, local_rank, world):
     pin_out = {k: torch.empty(cells, dtype=torch.float64).pin_memory() for k in outs}
     for k in ins:
         h.get_to(k, pin_in[k].data_ptr())
-    Ke = max(2, min(K, 3))
+    Ke = max(10, K)
     for k in ins:    # untimed: first use allocates the staging / snapshot buffers and the copy streams
         h.set_from_async(k, pin_in[k].data_ptr())
     for k in outs:
@@ -233,64 +324,92 @@ def run_b200(args, rank, local_rank, world):
         for k in outs:
             h.get_to_async(k, pin_out[k].data_ptr())
     barrier()   # hg_device_synchronize waits for the compute and both copy streams
-    e2e_sec = (time.perf_counter() - t0) / Ke
-    if dist is not None:
-        t = torch.tensor([e2e_sec], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_sec = float(t.item())
-    e2e = {"value": world * cells / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": len(ins) * cells * 8,
+    e2e_sec = allmax((time.perf_counter() - t0) / Ke)
+    e2e = {"value": total_cells / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": len(ins) * cells * 8,
            "d2h_bytes_per_step": len(outs) * cells * 8 + 8 * 40, "ms_per_step": e2e_sec * 1e3, "steps": Ke,
            "timing": "host wall clock around pinned H2D (hg_set_field_async) + hg_step + D2H (hg_get_field_async), all streams "
                      "synchronised at the end, max over ranks"}
+    kname = h.solver_kernel_name(0)
+    lu_name = h.solver_kernel_name(1)
+
+    # ---- the same mesh as configured (SURVEY 8d second accounting mode): <= 20 SIMPLE iterations (tol 1e-4), Gauss-Seidel
+    # <= 1000 sweeps with tol 1e-5 -- the sweep chunks are checked on the host, an overshooting chunk is replayed
+    asconf = None
+    if world == 1 and args.workload == "rt" and not args.no_as_configured:
+        h.close()
+        del pin_in, pin_out
+        ha = Hydro(workload_params(n, "rt", as_configured=True), device=local_rank)
+        ha.step()
+        ha.synchronize()
+        ha.event_record(0)
+        sts = [ha.step() for _ in range(2)]
+        ha.event_record(1)
+        ha.synchronize()
+        ams = ha.event_elapsed_ms(0, 1) / len(sts)
+        sim = sum(s_.simple_iterations for s_ in sts) / len(sts)
+        swp = sum(s_.pressure_sweeps_total for s_ in sts) / len(sts)
+        bp = 664. * sim + 32. * swp + 96. * sts[-1].advection_substeps + 120.
+        asconf = {"workload": "RT-3D %d^3 as configured: <= 20 SIMPLE iterations (tol 1e-4), gauss_seidel <= 1000 sweeps (tol 1e-5)" % n,
+                  "ms_per_step": ams, "value": cells / (ams * 1e-3), "unit": UNIT, "steps": len(sts),
+                  "simple_iterations_per_step": sim, "pressure_sweeps_per_step": swp,
+                  "algorithmic_bytes_per_cell_step": bp, "frac_of_peak": bp * cells / (ams * 1e-3) / 1e9 / measured_peak()[0]}
+        ha.close()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
     peak, peak_src = measured_peak()
-    # roofline of the dominant kernel: the Gauss-Seidel sweep kernel k_gs_tiled (time-skewed column boxes; on slabs the
-    # boxes of neighbouring GPUs exchange tagged interface values), one launch per pressure solve = (limit+1) sweeps x 32
+    # roofline of the dominant kernel: the Gauss-Seidel sweep kernel (time-skewed column boxes; on slabs the boxes of
+    # neighbouring GPUs exchange tagged interface values), one launch per pressure solve = (limit+1) sweeps x 32
     # algorithmic bytes per cell-sweep
     sweeps_per_solve = p["lu_relaxed_num_iters_limit"] + 1
     gs_bytes = 32.0 * sweeps_per_solve * cells
     gs_avg_ms = gs_ms / gs_n if gs_n else float("nan")
     achieved = gs_bytes / (gs_avg_ms * 1e-3) / 1e9 if gs_n else None
     bpcs = bytes_per_cell_step(n_simple, sweeps_per_solve, n_adv, False)
-    step_gbs = bpcs * cells / sec_step / 1e9
-    kname = ("k_gs_tiled (lexicographic Gauss-Seidel/SOR as time-skewed column boxes, rows staged by TMA, %d sweeps per launch)" if world == 1 else
-             "k_gs_tiled<LINK> (the same box dataflow on every z-slab, interface values as sweep-tagged peer stores, %d sweeps per launch)")
-    roof = {"bound": "hbm", "kernel": kname % sweeps_per_solve,
+    step_gbs = bpcs * total_cells / world / sec_step / 1e9
+    roof = {"bound": "hbm", "kernel": "%s (lexicographic Gauss-Seidel/SOR as time-skewed column boxes, rows of a hyperplane staged once per "
+                                      "box by TMA and shared by the sweeps in flight, %d sweeps per launch)" % (kname, sweeps_per_solve),
             "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
             "frac": achieved / peak if achieved else None, "traffic": None,
             "launches_timed": gs_n, "avg_launch_ms": gs_avg_ms, "share_of_step": gs_ms / ms if ms else None,
-            "lu_kernel_share_of_step": lu_ms / ms if ms else None,
-            "whole_step": {"algorithmic_bytes_per_cell_step": bpcs, "achieved": step_gbs, "frac": step_gbs / peak}}
+            "lu_kernel": lu_name, "lu_kernel_share_of_step": lu_ms / ms if ms else None,
+            "lu_avg_solve_ms": lu_ms / lu_n if lu_n else None,
+            "whole_step": {"algorithmic_bytes_per_cell_step": bpcs, "achieved_per_gpu": step_gbs, "frac": step_gbs / peak}}
     traffic_file = os.path.join(ROOT, "profiles", "gs_traffic.json")
     if os.path.exists(traffic_file):
         try:
-            if world == 1:
+            if world == 1 and args.workload == "rt":
                 roof["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch_scaled_to", {}).get(str(n))
         except Exception:
             pass
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            v, sec, info = cpu_reference_run(args.cpu_size, 2, 1)
-            info.update({"value": v, "unit": UNIT, "ms_per_step": sec * 1e3})
+            v, sec, info = cpu_reference_run(args.cpu_size, 5, 1)
+            info.update({"value": v, "unit": UNIT, "ms_per_step": sec * 1e3, "cpu_model": cpu_model()})
             cpu = info
         except Exception as e:  # the baseline is a report, never a gate
             cpu = {"error": str(e)[:200]}
+    wname = ("RT-3D %d^3 fixed-work: 3 SIMPLE iterations x (lu momentum + 101 GS sweeps) + 1 advection sub-step + properties + "
+             "stats per step (SURVEY 8d W4)" % n) if args.workload == "rt" else \
+            ("broken_dam_3d %d^3 (SURVEY 8d W5: obstacle box, 5 SIMPLE iterations x (lu momentum + 101 GS sweeps), 10 advection "
+             "sub-steps, smoothing 2/3/3)" % n)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": sec_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": sec_step * 1e3, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "RT-3D %d^3 fixed-work: 3 SIMPLE iterations x (lu momentum + 101 GS sweeps) + 1 advection "
-                                   "sub-step + properties + stats per step (SURVEY 8d W4)" % n,
+            "config": {"workload": wname, "mesh": list(mesh),
                        "cells_per_gpu": cells, "simple_iterations": n_simple, "pressure_sweeps_per_step": sweeps,
                        "advection_substeps": n_adv,
                        "parallelism": "1 GPU" if world == 1 else
                        "z-slabs over %d GPUs, one process per GPU: %dx%dx%d cells, halo planes / solver interface values / "
-                       "reductions over NVLink peer memory (weak scaling, %d^3 cells per GPU)" % ((world,) + mesh + (n,)),
+                       "reductions over NVLink peer memory (%s scaling)" % ((world,) + tuple(mesh) + ("strong" if strong else "weak, %d^3 cells per GPU" % n,)),
                        "l2": "working set %.1f GB per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)" % (cells * 8 * 90 / 1e9)},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+    if parity is not None:
+        line["parity_check"] = parity
+    if asconf is not None:
+        line["as_configured"] = asconf
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -305,6 +424,9 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--cpu-size", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-as-configured", action="store_true")
+    ap.add_argument("--workload", default="rt", choices=["rt", "dam"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -26,7 +26,8 @@ SYMBOLS = [
     "hg_update_properties", "hg_calc_stat", "hg_interp_grad", "hg_linear_solve", "hg_smooth_field",
     "hg_timers", "hg_timers_enable", "hg_launch_count", "hg_device_synchronize", "hg_event_record",
     "hg_event_elapsed_ms", "hg_profile_enable", "hg_profile_read",
-    "hg_ipc_record_size", "hg_ipc_export", "hg_ipc_import", "hg_link_local",
+    "hg_ipc_record_size", "hg_ipc_export", "hg_ipc_import", "hg_link_local", "hg_get_stats", "hg_solver_kernel_name",
+    "hg_profile_read_clocks",
 ]
 
 
@@ -63,6 +64,10 @@ def load_library():
     l.hg_fluid_auto_time_step.argtypes = [C.c_void_p, dp]
     l.hg_set_time_step.argtypes = [C.c_void_p, C.c_double, C.c_double]
     l.hg_calc_stat.argtypes = [C.c_void_p, C.POINTER(HgStepStats)]
+    l.hg_get_stats.argtypes = [C.c_void_p, C.POINTER(HgStepStats)]
+    l.hg_profile_read_clocks.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
+    l.hg_solver_kernel_name.argtypes = [C.c_void_p, C.c_int]
+    l.hg_solver_kernel_name.restype = C.c_char_p
     l.hg_interp_grad.argtypes = [C.c_void_p, dp, C.c_int, C.c_int, dp, dp, dp]
     l.hg_linear_solve.argtypes = [C.c_void_p, C.c_int, C.POINTER(dp), dp, dp, C.c_double, C.c_int, C.c_double,
                                   C.POINTER(C.c_int), dp]
@@ -212,6 +217,14 @@ class Hydro:
         self._chk(self.l.hg_calc_stat(self.h, C.byref(st)))
         return st
 
+    def get_stats(self):
+        st = HgStepStats()
+        self._chk(self.l.hg_get_stats(self.h, C.byref(st)))
+        return st
+
+    def solver_kernel_name(self, which=0):
+        return self.l.hg_solver_kernel_name(self.h, which).decode()
+
     # -- kernel-level entries ---------------------------------------------------------
     def interp_grad(self, u, cond, comp=0):
         u = np.ascontiguousarray(u, dtype=np.float64)
@@ -264,6 +277,11 @@ class Hydro:
         ms = C.c_double()
         self._chk(self.l.hg_profile_read(self.h, which, C.byref(n), C.byref(ms)))
         return n.value, ms.value
+
+    def profile_read_clocks(self):
+        out = (C.c_ulonglong * 16)()
+        self._chk(self.l.hg_profile_read_clocks(self.h, out))
+        return list(out)
 
     def get_into(self, name, buf):
         """hg_get_field into a caller-provided (e.g. pinned) float64 buffer."""

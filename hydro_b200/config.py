@@ -51,7 +51,6 @@ class HgConfig(C.Structure):
         ("heat_box_lb", d3), ("heat_box_rt", d3), ("heat_box_temperature", C.c_double),
         ("heat_relaxation_factor", C.c_double), ("time_second_order_heat", C.c_int),
         ("world_size", C.c_int), ("rank", C.c_int), ("device", C.c_int),
-        ("nccl_unique_id", C.c_void_p),
         ("pressure_sweeps_per_check", C.c_int), ("solver_ctas", C.c_int), ("reserved", C.c_int * 6),
     ]
 
@@ -442,8 +441,9 @@ class Params(dict):
         return self
 
     # -- struct -----------------------------------------------------------------
-    def to_struct(self, world_size=1, rank=0, device=0, nccl_unique_id=None, solver_ctas=0):
+    def to_struct(self, world_size=1, rank=0, device=0, solver_ctas=0):
         p = self
+        reject_unsupported(p)
 
         def need(k):
             if k not in p:
@@ -504,9 +504,6 @@ class Params(dict):
         if need("advection_solver") != "tvd":
             raise ValueError("only advection_solver tvd is on the GPU path")
         c.world_size, c.rank, c.device = world_size, rank, device
-        if nccl_unique_id is not None:
-            self._uid_buf = C.create_string_buffer(bytes(nccl_unique_id), 128)
-            c.nccl_unique_id = C.cast(self._uid_buf, C.c_void_p)
         c.pressure_sweeps_per_check = int(p.get("pressure_sweeps_per_check", 0))
         c.solver_ctas = int(solver_ctas)
         return c
@@ -527,6 +524,26 @@ class Params(dict):
                 typ = "bool" if (k in _BOOL_KEYS or GENERAL_TYPES.get(k) == "bool") else "int"
                 out.append("set %s %s %d" % (typ, k, int(v)))
         return out
+
+
+def reject_unsupported(p):
+    """Options that change the reference's results but are not on the GPU path fail loudly instead of being
+    dropped (hydro2d.hpp:326-368 initial images / deforming velocity, 1030-1122 phase slip, 1129/1387 compressibility,
+    1163-1185 chemistry, 1294 radiation, 1511-1524 automatic mesh velocity)."""
+    def truthy(k):
+        v = p.get(k, 0)
+        return bool(int(v)) if not isinstance(v, str) else v not in ("", "0")
+    for k in ("compressible_enable", "deforming_velocity", "radiation_enable"):
+        if truthy(k):
+            raise ValueError("%s 1 is not on the GPU path" % k)
+    if str(p.get("chemistry", "steady")) != "steady" or float(p.get("chem_intensity", 0.0)) != 0.0:
+        raise ValueError("chemistry other than 'steady' with chem_intensity 0 is not on the GPU path")
+    for k in ("meshvel_auto", "imgu_init", "imgv_init", "img_init"):
+        if k in p:
+            raise ValueError("%s is not on the GPU path" % k)
+    for i in range(HG_MAX_PHASES):
+        if truthy("enable_settling_%d" % i):
+            raise ValueError("phase slip (enable_settling_%d) is not on the GPU path" % i)
 
 
 _DOUBLE_KEYS = {"initial_sin_lambda", "initial_sin_phase", "pressure_fixed_value", "T", "dt",

@@ -53,6 +53,32 @@ __global__ void k_nan_flag(const double* __restrict__ a, long long n, int* flag)
   if (t < n && !(a[t] * 0. == 0.)) *flag = 1;
 }
 
+// `iter` and `diff` of a finished Gauss-Seidel solve from its per-sweep norms: the loop
+// `do { sweep } while (diff > tol && iter++ < limit)` (linear.hpp:688-710) stops at the first sweep whose norm is not
+// above the tolerance.  out = {iter, diff}.  With tol == 0 the sweeps after that one are fixed points (all corrections
+// are exactly zero), so running all limit+1 sweeps leaves the same solution and only the reported count differs.
+__global__ void k_sor_result(const double* __restrict__ diffs, int max_total, double tol, double* __restrict__ out) {
+  int stop = -1;
+  for (int k = 0; k < max_total; ++k) if (!(diffs[k] > tol)) { stop = k; break; }
+  out[0] = stop >= 0 ? (double)stop : (double)max_total;   // `iter++ < limit` increments even when it fails
+  out[1] = stop >= 0 ? diffs[stop] : diffs[max_total - 1];
+}
+// End of a time step: everything the host wants to know, as doubles behind the statistics (one transfer, one wait):
+// out[0..7] NaN flags, [8] / [9] abort words of the sweep / lu dataflow kernels, [10] convergence indicator of the last
+// SIMPLE iteration, [11] sum of iter+1 over the step's deferred pressure solves, [12] diff of the last one
+__global__ void k_status_pack(const int* __restrict__ nanflags, const int* gt_ctl, const int* lt_ctl, const double* __restrict__ resid_last,
+                              const double* __restrict__ sorres, int nsolves, double* __restrict__ out) {
+  if (threadIdx.x < 8) out[threadIdx.x] = nanflags[threadIdx.x] ? 1. : 0.;
+  if (threadIdx.x == 8) out[8] = gt_ctl ? (double)gt_ctl[1] : 0.;
+  if (threadIdx.x == 9) out[9] = lt_ctl ? (double)lt_ctl[1] : 0.;
+  if (threadIdx.x == 10) out[10] = resid_last ? *resid_last : 1.;
+  if (threadIdx.x == 11) {
+    double sum = 0., last = 0.;
+    for (int m = 0; m < nsolves; ++m) { sum += sorres[2 * m] + 1.; last = sorres[2 * m + 1]; }
+    out[11] = sum; out[12] = last;
+  }
+}
+
 // ---------------------------------------------------------------- GetSmoothField
 // One repeat of Average(Interpolate(u, zero-derivative)) (solver.hpp:621-656)
 template <int DIM>

@@ -32,6 +32,7 @@ struct hg_state {
   cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
   std::map<int, double*> xfer_stage, xfer_snap;
   std::map<int, cudaEvent_t> xfer_ev;
+  cudaEvent_t xfer_ev_tmp[2] = {nullptr, nullptr};   // ordering events of the asynchronous transfers (created once)
   int dim = 0, n[3] = {1, 1, 1};
   long long nc = 0, nf = 0, nsh = 0;
   Geo geo;
@@ -50,18 +51,27 @@ struct hg_state {
   // time-skewed tile sweeps (hg_gs_tiled.cuh): explicit diagonal, task lists per number of sweeps in a launch
   bool gs_tiled = false;
   double* DGs = nullptr;
-  double2* CO = nullptr; long long co_n = 0;   // packed rows of k_gs_tiled (gt_co_index), co_n double2 per array
+  double* CO = nullptr; Co5 co5;               // rows of k_gs_tiled: five hyperplane-major arrays (gt_co5_index)
   CUtensorMap tmco;
-  struct GtPlan { int ntasks = 0; GtTask* tasks = nullptr; int* progress = nullptr; };
-  std::map<int, GtPlan> gt_plans;
+  // task lists of k_gs_tiled per number of sweeps in a launch: GT_PLAN_SLOTS device buffers sized for the largest launch,
+  // allocated at creation (no allocation on the stepping path), reused least-recently-used
+  struct GtPlan { int S = -1, ntasks = 0; GtTask* tasks = nullptr; int* progress = nullptr; GtTask* stage = nullptr; cudaEvent_t staged = nullptr; long long used = 0; };
+  static constexpr int GT_PLAN_SLOTS = 4;
+  GtPlan gt_plans[GT_PLAN_SLOTS];
+  int gt_plan_cap = 0; long long gt_plan_clock = 0;
   int* gt_ctl = nullptr;
+  unsigned long long* gt_clk = nullptr;
   // lu as a dataflow of column boxes (hg_lu_tiled.cuh)
   bool lu_tiled = false; int2* lt_boxes = nullptr; int lt_nboxes = 0, lt_nbi = 0; int* lt_progress = nullptr; int* lt_ctl = nullptr;
   int num_sms = 0;
   double* resid = nullptr;    // per-iteration convergence indicators of the current step (device, 4096)
   double* scal = nullptr;     // device scalars: [0] resid, [1] auto dt, [2..] stat (36), then diffs
-  int* flag = nullptr;        // NaN flag
+  int* flag = nullptr;        // [0] scratch NaN flag (immediate checks), [1] any-excluded flag, [4..11] deferred NaN flags of a step
+  bool defer = false;         // inside hg_step: NaN flags, solver status words, sweep counts and statistics are read once, at the end
+  double* sorres = nullptr;   // per pressure solve of the step: {iter, diff} computed on the device (deferred mode)
+  int nsolves = 0;
   double* hscal = nullptr;    // pinned host mirror
+  double* hinit = nullptr;    // pinned: initial values of the statistics accumulators
   int max_sweeps = 0;
   double* diffs = nullptr;    // per-sweep max norms (device)
   double* hdiffs = nullptr;   // pinned
@@ -284,8 +294,11 @@ static int ensure_sweep_capacity(hg_state* s, int nsweeps) {
 // Runs `do { sweep } while (diff > tol && iter++ < limit)` (linear.hpp:688-710) with pipelined sweeps.
 // launch(s_begin, s_end) must run sweeps [s_begin, s_end) on x; save/restore checkpoint x when a
 // chunk overshoots the stopping sweep.  Returns the reference's `iter` and `diff`.
+// defer_out != nullptr (one GPU, tol == 0): nothing is read back -- {iter, diff} are written to defer_out on the device
+// (k_sor_result) and *out_iter = -1.
 template <class LaunchFn>
-static int run_sor(hg_state* s, double* x, long long nx_, double tol, int limit, LaunchFn launch, int* out_iter, double* out_diff) {
+static int run_sor(hg_state* s, double* x, long long nx_, double tol, int limit, LaunchFn launch, int* out_iter, double* out_diff,
+                   double* defer_out = nullptr) {
   const int max_total = limit + 1;
   if (int rc = ensure_sweep_capacity(s, max_total)) return rc;
   CK(cudaMemsetAsync(x, 0, nx_ * sizeof(double), s->st));
@@ -300,6 +313,14 @@ static int run_sor(hg_state* s, double* x, long long nx_, double tol, int limit,
     return slab_sync(s);
   };
   if (int rc = ll_reset()) return rc;
+  if (!(tol > 0.) && defer_out && s->world == 1) {
+    // `diff > tol` only fails for diff == 0: from that sweep on every correction is exactly zero, so running all
+    // limit+1 sweeps leaves the same solution; the count the reference would report is derived on the device
+    for (int sb = 0; sb < max_total; sb += SOLVER_SC) if (int rc = launch(sb, std::min(sb + SOLVER_SC, max_total))) return rc;
+    LAUNCH(s, k_sor_result, 1, 1, s->diffs, max_total, tol, defer_out);
+    *out_iter = -1; *out_diff = 0.;
+    return 0;
+  }
   if (!(tol > 0.)) {
     // `diff > tol` only fails for diff == 0 (or NaN): run all limit+1 sweeps, inspect the history once
     for (int sb = 0; sb < max_total; sb += SOLVER_SC) {
@@ -424,11 +445,14 @@ static int run_lu_relaxed(hg_state* s, const double* R, double* res, double* cor
 }
 
 // Task list of k_gs_tiled for a launch of S sweeps: boxes (I, J, group) sorted by the step at which they can start,
-// 32 I + 15 J + 65 group (a box starts 32 / 15 steps after its left / lower neighbour and 2B+1 steps after the box
+// TX I + TY J + (TX + TY + 2B + 2) group (a box starts TX / TY steps after its left / lower neighbour and 2B+1 steps after the box
 // (I+1, J+1) of the previous group), which also puts every dependency of a box before it (own group: (I-1,J), (I,J-1), (I-1,J-1); previous group: (I..I+1, J..J+1)).
-static int gt_plan(hg_state* s, int S, hg_state::GtPlan** out) {
-  auto it = s->gt_plans.find(S);
-  if (it != s->gt_plans.end()) { *out = &it->second; return 0; }
+static int gt_num_tasks(const hg_state* s, int S) {
+  const int nx = s->n[0], ny = s->n[1];
+  const int NG = (S + GT_B - 1) / GT_B, NI = (nx + GT_B - 1 + GT_TX - 1) / GT_TX, NJ = (ny + GT_B - 1 + GT_TY - 1) / GT_TY;
+  return NG * NI * NJ;   // upper bound (boxes without cells are dropped)
+}
+static int gt_build_tasks(hg_state* s, int S, GtTask* tasks, int* ntasks) {
   const int nx = s->n[0], ny = s->n[1], nz = s->n[2];
   const int NG = (S + GT_B - 1) / GT_B, NI = (nx + GT_B - 1 + GT_TX - 1) / GT_TX, NJ = (ny + GT_B - 1 + GT_TY - 1) / GT_TY;
   struct Key { int w, gI, J, I; };
@@ -445,7 +469,6 @@ static int gt_plan(hg_state* s, int S, hg_state::GtPlan** out) {
   std::vector<int> index((size_t)NG * NJ * NI, -1);
   auto at = [&](int I, int J, int gI) -> int { return exists(I, J, gI) ? index[((size_t)gI * NJ + J) * NI + I] : -1; };
   for (size_t q = 0; q < keys.size(); ++q) index[((size_t)keys[q].gI * NJ + keys[q].J) * NI + keys[q].I] = (int)q;
-  std::vector<GtTask> tasks(keys.size());
   for (size_t q = 0; q < keys.size(); ++q) {
     const Key& k = keys[q];
     GtTask& t = tasks[q];
@@ -457,13 +480,42 @@ static int gt_plan(hg_state* s, int S, hg_state::GtPlan** out) {
     t.dep[5] = at(k.I, k.J + 1, k.gI - 1); t.dep[6] = at(k.I + 1, k.J + 1, k.gI - 1);
     for (int d = 0; d < GT_MAXDEP; ++d) if (t.dep[d] >= (int)q) { s->err = "gt_plan: dependency order violated"; return HG_ERR_INVALID; }
   }
-  hg_state::GtPlan pl;
-  pl.ntasks = (int)tasks.size();
-  if (dalloc(s, &pl.tasks, pl.ntasks, false) || dalloc(s, &pl.progress, pl.ntasks, true)) return HG_ERR_CUDA;
-  CK(cudaMemcpyAsync(pl.tasks, tasks.data(), tasks.size() * sizeof(GtTask), cudaMemcpyHostToDevice, s->st));
-  CK(cudaStreamSynchronize(s->st));   // `tasks` goes out of scope
-  s->gt_plans[S] = pl;
-  *out = &s->gt_plans[S];
+  *ntasks = (int)keys.size();
+  return 0;
+}
+// largest number of sweeps a launch of this handle can have (run_sor chunks)
+static int gt_max_launch_sweeps(const hg_state* s) {
+  const int max_total = s->cfg.lu_relaxed_num_iters_limit + 1;
+  int chunk = SOLVER_SC;
+  if (s->cfg.lu_relaxed_tolerance > 0.) {
+    chunk = s->cfg.pressure_sweeps_per_check > 0 ? s->cfg.pressure_sweeps_per_check : 128;
+    if (chunk > SOLVER_SC) chunk = SOLVER_SC;
+  }
+  return std::max(1, std::min(chunk, max_total));
+}
+static int gt_plans_allocate(hg_state* s) {   // at creation
+  s->gt_plan_cap = gt_num_tasks(s, gt_max_launch_sweeps(s));
+  for (auto& pl : s->gt_plans) {
+    if (dalloc(s, &pl.tasks, s->gt_plan_cap, false) || dalloc(s, &pl.progress, s->gt_plan_cap, true)) return HG_ERR_CUDA;
+    CK(cudaMallocHost((void**)&pl.stage, (size_t)s->gt_plan_cap * sizeof(GtTask)));
+    CK(cudaEventCreateWithFlags(&pl.staged, cudaEventDisableTiming));
+  }
+  return 0;
+}
+static int gt_plan(hg_state* s, int S, hg_state::GtPlan** out) {
+  hg_state::GtPlan* lru = &s->gt_plans[0];
+  for (auto& pl : s->gt_plans) {
+    if (pl.S == S) { pl.used = ++s->gt_plan_clock; *out = &pl; return 0; }
+    if (pl.used < lru->used) lru = &pl;
+  }
+  if (gt_num_tasks(s, S) > s->gt_plan_cap) { s->err = "gt_plan: launch larger than the preallocated task list"; return HG_ERR_INVALID; }
+  // the pinned staging buffer of this slot may still be read by its previous upload
+  CK(cudaEventSynchronize(lru->staged));
+  if (int rc = gt_build_tasks(s, S, lru->stage, &lru->ntasks)) return rc;
+  CK(cudaMemcpyAsync(lru->tasks, lru->stage, (size_t)lru->ntasks * sizeof(GtTask), cudaMemcpyHostToDevice, s->st));
+  CK(cudaEventRecord(lru->staged, s->st));
+  lru->S = S; lru->used = ++s->gt_plan_clock;
+  *out = lru;
   return 0;
 }
 static int gt_launch(hg_state* s, int sb, int se, double omega) {
@@ -473,6 +525,7 @@ static int gt_launch(hg_state* s, int sb, int se, double omega) {
   a.s_begin = sb; a.omega = omega; a.tasks = pl->tasks; a.ntasks = pl->ntasks; a.progress = pl->progress; a.ctl = s->gt_ctl;
   a.lag_prev = 2 * GT_B + 1;
   a.PS8 = 8LL * s->n[0] * s->n[1]; a.DSH8 = 8LL * (2LL * s->n[0] * s->n[1] + s->n[0] + 1);
+  a.clk = s->gt_clk;
   CK(cudaMemsetAsync(pl->progress, 0, pl->ntasks * sizeof(int), s->st));
   CK(cudaMemsetAsync(s->gt_ctl, 0, sizeof(int), s->st));   // next-task counter; the abort flag [1] is sticky
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -512,9 +565,9 @@ static int solve_pressure(hg_state* s) {
       return s->any_excl ? coop_launch(s, k_gs_persistent<2, true>, s->grid_solver, s->geo, a, 0)
                          : coop_launch(s, k_gs_persistent<2, false>, s->grid_solver, s->geo, a, 0);
     };
-    if (int rc = run_sor(s, s->PP, s->nsh, c.lu_relaxed_tolerance, c.lu_relaxed_num_iters_limit, launch, &it, &df)) return rc;
-    if (s->gs_tiled) if (int rc = gt_check(s)) return rc;
-    if (s->lu_tiled) if (int rc = lt_check(s)) return rc;
+    double* defer_out = (s->defer && s->world == 1 && s->nsolves < 4096) ? s->sorres + 2 * s->nsolves : nullptr;
+    if (int rc = run_sor(s, s->PP, s->nsh, c.lu_relaxed_tolerance, c.lu_relaxed_num_iters_limit, launch, &it, &df, defer_out)) return rc;
+    if (!s->defer && s->gs_tiled) if (int rc = gt_check(s)) return rc;   // inside hg_step: part of the step's status block
     DIMSEL(s, k_pcorr, nblk(s->nc), 256, s->geo, s->PP, s->p[L_IP], c.pressure_relaxation_factor, s->pc, s->p[L_IC]);
   } else if (c.linear_solver_pressure == HG_LS_JACOBI) {
     // natural layout: constants back from the sheared array, rows regenerated from d_c
@@ -541,7 +594,9 @@ static int solve_pressure(hg_state* s) {
     s->err = "linear_solver_pressure: lu is not iterated for the pressure system on the GPU path";
     return HG_ERR_INVALID;
   }
-  s->sweeps_total += it + 1; s->last_diff = df;
+  if (!s->defer && s->lu_tiled) if (int rc = lt_check(s)) return rc;   // the momentum solve's dataflow kernel
+  if (it < 0) ++s->nsolves;   // deferred: counted on the device, added at the end of the step
+  else { s->sweeps_total += it + 1; s->last_diff = df; }
   return 0;
 }
 
@@ -652,43 +707,54 @@ extern "C" int hg_update_properties(hg_handle s) {
   return 0;
 }
 
-extern "C" int hg_calc_stat(hg_handle s, hg_step_stats* st) {
-  if (!s) return HG_ERR_INVALID;
-  cudaSetDevice(s->dev);
+// CalcStat (hydro2d.hpp:1432-1529).  with_status (end of hg_step): the step's status block (NaN flags, abort words of the
+// dataflow kernels, last convergence indicator, deferred sweep counts) travels behind the 36 statistics values in the
+// same transfer / the same rank-ordered reduction, so a step waits for the device once.
+enum { ST_STAT = 2, ST_STATUS = 38, ST_TOTAL = 51 };   // offsets in s->scal / s->hscal
+static int calc_stat(hg_state* s, hg_step_stats* st, bool with_status) {
   const hg_config& c = s->cfg;
   double init[36];
   for (int p = 0; p < 3; ++p) { for (int q = 0; q < 12; ++q) init[p * 12 + q] = 0.; init[p * 12 + 7] = 1e10; init[p * 12 + 8] = -1e10; }
-  CK(cudaMemcpyAsync(s->scal + 2, init, sizeof(init), cudaMemcpyHostToDevice, s->st));
+  memcpy(s->hinit, init, sizeof init);   // pinned: the async copy reads it when the stream gets there
+  CK(cudaMemcpyAsync(s->scal + ST_STAT, s->hinit, sizeof(init), cudaMemcpyHostToDevice, s->st));
   StatArgs a; a.np = c.num_phases;
   for (int p = 0; p < 3; ++p) { a.vf[p] = s->vf[p]; a.pd[p] = s->pd[p][L_TC]; }
   for (int d = 0; d < 3; ++d) a.u[d] = s->u[L_TC][d] ? s->u[L_TC][d] : s->zero;
-  a.out = s->scal + 2;
+  a.out = s->scal + ST_STAT;
   DIMSEL(s, k_stat, nblk(s->nc), 256, s->geo, a);
+  int nvals = 36;
+  if (with_status) {
+    const double* rl = s->iter_count > 0 ? s->resid + (s->iter_count - 1 < 4095 ? s->iter_count - 1 : 4095) : nullptr;
+    LAUNCH(s, k_status_pack, 1, 32, s->flag + 4, s->gs_tiled ? s->gt_ctl : nullptr, s->lu_tiled ? s->lt_ctl : nullptr, rl, s->sorres,
+           s->nsolves, s->scal + ST_STATUS);
+    nvals = ST_TOTAL - ST_STAT;
+  }
   if (s->world > 1) {   // sums in rank order; minima / maxima
     std::vector<double> all;
-    if (int rc = slab_gather(s, s->scal + 2, 36, all)) return rc;
-    for (int q = 0; q < 36; ++q) {
+    if (int rc = slab_gather(s, s->scal + ST_STAT, nvals, all)) return rc;
+    for (int q = 0; q < nvals; ++q) {
       double v = all[q];
       for (int r = 1; r < s->world; ++r) {
-        const double w = all[(size_t)r * 36 + q];
-        v = (q % 12 == 7) ? (w < v ? w : v) : (q % 12 == 8) ? (v < w ? w : v) : v + w;
+        const double w = all[(size_t)r * nvals + q];
+        if (q >= 36) v = v < w ? w : v;   // status words: maximum
+        else v = (q % 12 == 7) ? (w < v ? w : v) : (q % 12 == 8) ? (v < w ? w : v) : v + w;
       }
-      s->hscal[2 + q] = v;
+      s->hscal[ST_STAT + q] = v;
     }
   } else {
-    CK(cudaMemcpyAsync(s->hscal + 2, s->scal + 2, 36 * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    CK(cudaMemcpyAsync(s->hscal + ST_STAT, s->scal + ST_STAT, nvals * sizeof(double), cudaMemcpyDeviceToHost, s->st));
     CK(cudaStreamSynchronize(s->st));
   }
   hg_step_stats& o = s->stat;
   for (int p = 0; p < c.num_phases; ++p) {
-    const double* r = s->hscal + 2 + p * 12;
+    const double* r = s->hscal + ST_STAT + p * 12;
     o.volume[p] = r[0]; o.mass[p] = r[0] * c.density[p]; o.pd_min[p] = r[7]; o.pd_max[p] = r[8];
     for (int d = 0; d < 3; ++d) {
       o.center[p][d] = d < s->dim ? r[1 + d] / r[0] + s->meshpos[d] : 0.;
       o.velocity[p][d] = d < s->dim ? r[4 + d] / r[0] : 0.;
     }
   }
-  if (c.meshvel_output) for (int d = 0; d < s->dim; ++d) s->meshpos[d] += c.meshvel[d] * s->dt;
+  if (c.meshvel_output) for (int d = 0; d < s->dim; ++d) s->meshpos[d] += c.meshvel[d] * s->dt;   // hydro2d.hpp:1526-1528
   if (st) {
     for (int p = 0; p < HG_MAX_PHASES; ++p) {
       st->volume[p] = o.volume[p]; st->mass[p] = o.mass[p]; st->pd_min[p] = o.pd_min[p]; st->pd_max[p] = o.pd_max[p];
@@ -697,9 +763,25 @@ extern "C" int hg_calc_stat(hg_handle s, hg_step_stats* st) {
   }
   return 0;
 }
+extern "C" int hg_calc_stat(hg_handle s, hg_step_stats* st) {
+  if (!s) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  return calc_stat(s, st, false);
+}
+extern "C" int hg_get_stats(hg_handle s, hg_step_stats* st) {
+  if (!s || !st) return HG_ERR_INVALID;
+  *st = s->stat;
+  return 0;
+}
 
 // ------------------------------------------------------------------ fluid solver protocol
-static int check_nan(hg_state* s, const double* a, long long n, const char* msg) {
+enum { NF_INIT_P = 0, NF_INIT_U = 1, NF_FIN_P = 2, NF_FIN_U = 3, NF_HEAT_INIT = 4, NF_HEAT_FIN = 5, NF_COUNT = 8 };
+static const char* const nan_msgs[NF_COUNT] = {"NaN initial pressure", "NaN initial field", "NaN pressure", "NaN field",
+                                               "NaN initial field", "NaN field", "", ""};
+// IsNan scan of a field (solver.hpp:17-30).  Inside hg_step the flag is only raised (slot `which` of the step's status
+// block, read once at the end of the step); called through the fine-grained entries it is checked at once.
+static int check_nan(hg_state* s, const double* a, long long n, int which) {
+  if (s->defer) { LAUNCH(s, k_nan_flag, nblk(n), 256, a, n, s->flag + 4 + which); return 0; }
   CK(cudaMemsetAsync(s->flag, 0, sizeof(int), s->st));
   LAUNCH(s, k_nan_flag, nblk(n), 256, a, n, s->flag);
   int h = 0;
@@ -712,7 +794,7 @@ static int check_nan(hg_state* s, const double* a, long long n, const char* msg)
     CK(cudaMemcpyAsync(&h, s->flag, sizeof(int), cudaMemcpyDeviceToHost, s->st));
     CK(cudaStreamSynchronize(s->st));
   }
-  if (h) { s->err = msg; return HG_ERR_NAN; }
+  if (h) { s->err = nan_msgs[which]; return HG_ERR_NAN; }
   return 0;
 }
 
@@ -723,10 +805,10 @@ extern "C" int hg_fluid_start_step(hg_handle s) {   // fluid.hpp:793-812
   CK(cudaMemsetAsync(s->resid, 0, 4096 * sizeof(double), s->st));
   // slabs: the caller may have set density / viscosity / force since the last hg_update_properties
   XCH(s, 1, s->rho, s->mu, s->force[0], s->force[1], s->dim > 2 ? s->force[2] : nullptr);
-  if (int rc = check_nan(s, s->p[L_TC], s->nc, "NaN initial pressure")) return rc;
+  if (int rc = check_nan(s, s->p[L_TC], s->nc, NF_INIT_P)) return rc;
   const double ge = s->cfg.guess_extrapolation;
   for (int d = 0; d < s->dim; ++d) {
-    if (int rc = check_nan(s, s->u[L_TC][d], s->nc, "NaN initial field")) return rc;
+    if (int rc = check_nan(s, s->u[L_TC][d], s->nc, NF_INIT_U)) return rc;
     LAUNCH(s, k_start_layer, nblk(s->nc), 256, s->u[L_IC][d], s->u[L_TC][d], s->u[L_TP][d], ge, s->nc);
   }
   LAUNCH(s, k_start_layer, nblk(s->nc), 256, s->p[L_IC], s->p[L_TC], s->p[L_TP], ge, s->nc);
@@ -779,7 +861,6 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
       k_assemble<2, K_VEL, 2><<<gb, 256, 0, s->st>>>(s->geo, a);
       ++s->launches;
     }
-    if (c.linear_solver_velocity != HG_LS_LU) { s->err = "linear_solver_velocity: only lu runs on the GPU path"; return HG_ERR_INVALID; }
     if (int rc = solve_lu(s, s->dim)) return rc;
     if (s->dim == 3) { k_apply_corr<3, 3><<<gb, 256, 0, s->st>>>(s->geo, cp3(s->u[L_IP]), cp3(s->X), p3(s->u[L_IC])); }
     else { k_apply_corr<2, 2><<<gb, 256, 0, s->st>>>(s->geo, cp3(s->u[L_IP]), cp3(s->X), p3(s->u[L_IC])); }
@@ -797,14 +878,16 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
     DIMSEL(s, k_prhs, gb, 256, s->geo, s->Fs, s->dc, 0, s->An[0], s->An[1], s->An[2], s->An[3], s->gs_tiled ? s->An[4] : nullptr);
     if (s->gs_tiled) {
       // natural -> packed rows of k_gs_tiled in one pass (transpose + packing)
-      GtPackArgs pa; pa.RP = s->An[0]; pa.CX = s->An[1]; pa.CY = s->An[2]; pa.CZ = s->An[3]; pa.DG = s->An[4]; pa.CO = s->CO; pa.dc = s->dc;
+      GtPackArgs pa; pa.in[0] = s->An[0]; pa.in[1] = s->An[4]; pa.in[2] = s->An[1]; pa.in[3] = s->An[2]; pa.in[4] = s->An[3];
+      pa.CO = s->CO; pa.dc = s->dc; pa.co = s->co5;
       k_gt_shear_pack<<<dim3((s->n[0] + 31) / 32, s->n[1], (s->n[2] + 31) / 32), 256, 0, s->st>>>(s->geo, pa);
       ++s->launches;
+      if (s->geo.zlo > 0) { k_gt_cz_halo<<<nblk(s->nxy), 256, 0, s->st>>>(s->geo, s->dc, s->CO, s->co5); ++s->launches; }
     } else {
       double* outs[4] = {s->RP, s->D, s->CYs, s->CZs};
       shear_arrays(s, s->An, outs, 4);
     }
-    if (s->geo.zlo > 0) { k_cz_halo<3><<<nblk(s->nxy), 256, 0, s->st>>>(s->geo, s->dc, s->CZs); ++s->launches; }
+    if (s->geo.zlo > 0 && !s->gs_tiled) { k_cz_halo<3><<<nblk(s->nxy), 256, 0, s->st>>>(s->geo, s->dc, s->CZs); ++s->launches; }
   } else {
     DIMSEL(s, k_prhs, gb, 256, s->geo, s->Fs, s->dc, 1, s->RP, s->D, s->CYs, s->CZs, nullptr);
   }
@@ -859,8 +942,8 @@ extern "C" int hg_fluid_finish_step(hg_handle s) {   // fluid.hpp:1159-1169, con
   rot(s->p[L_TC], s->p[L_TP], s->p[L_IC]);
   rot(s->F[L_TC], s->F[L_TP], s->F[L_IC]);
   for (int d = 0; d < s->dim; ++d) rot(s->u[L_TC][d], s->u[L_TP][d], s->u[L_IC][d]);
-  if (int rc = check_nan(s, s->p[L_TC], s->nc, "NaN pressure")) return rc;
-  for (int d = 0; d < s->dim; ++d) if (int rc = check_nan(s, s->u[L_TC][d], s->nc, "NaN field")) return rc;
+  if (int rc = check_nan(s, s->p[L_TC], s->nc, NF_FIN_P)) return rc;
+  for (int d = 0; d < s->dim; ++d) if (int rc = check_nan(s, s->u[L_TC][d], s->nc, NF_FIN_U)) return rc;
   s->time_fluid += s->dt;
   return 0;
 }
@@ -912,8 +995,7 @@ extern "C" int hg_heat_step(hg_handle s) {   // heat.hpp:69-84 + conv_diff.hpp:1
   if (!s) return HG_ERR_INVALID;
   cudaSetDevice(s->dev);
   const hg_config& c = s->cfg;
-  if (c.linear_solver_heat != HG_LS_LU) { s->err = "linear_solver_heat: only lu runs on the GPU path"; return HG_ERR_INVALID; }
-  if (int rc = check_nan(s, s->T[L_TC], s->nc, "NaN initial field")) return rc;
+  if (int rc = check_nan(s, s->T[L_TC], s->nc, NF_HEAT_INIT)) return rc;
   const unsigned gb = nblk(s->nc);
   // gradient of the temperature for the deferred upwind correction (conv_diff.hpp:135)
   P3 g3; for (int d = 0; d < 3; ++d) g3.p[d] = s->G[d];
@@ -939,17 +1021,14 @@ extern "C" int hg_heat_step(hg_handle s) {   // heat.hpp:69-84 + conv_diff.hpp:1
   ++s->launches;
   // FinishStep: time_prev <- time_curr <- iter_curr
   double* o = s->T[L_TP]; s->T[L_TP] = s->T[L_TC]; s->T[L_TC] = s->T[L_IC]; s->T[L_IC] = o;
-  if (int rc = check_nan(s, s->T[L_TC], s->nc, "NaN field")) return rc;
+  if (int rc = check_nan(s, s->T[L_TC], s->nc, NF_HEAT_FIN)) return rc;
+  if (!s->defer && s->lu_tiled) if (int rc = lt_check(s)) return rc;
   return 0;
 }
 
-extern "C" int hg_step(hg_handle s, hg_step_stats* stats) {   // hydro2d.hpp:1531-1621
-  if (!s) return HG_ERR_INVALID;
-  cudaSetDevice(s->dev);
+static int step_body(hg_state* s, int* nadv_out) {
   const hg_config& c = s->cfg;
   int rc;
-  tpush(s, "step");
-  s->sweeps_total = 0;
   if (c.dt_auto) {
     double dtm; if ((rc = hg_fluid_auto_time_step(s, &dtm))) return rc;
     s->dt = dtm * c.cfl; s->dt_adv = dtm * c.cfl_advection;
@@ -973,11 +1052,33 @@ extern "C" int hg_step(hg_handle s, hg_step_stats* stats) {   // hydro2d.hpp:153
   }
   if (c.heat_enable) { tpush(s, "step.heat"); if ((rc = hg_heat_step(s))) return rc; tpop(s); }
   if ((rc = hg_update_properties(s))) return rc;
-  if ((rc = hg_calc_stat(s, nullptr))) return rc;
-  tpop(s);
+  *nadv_out = nadv;
+  return calc_stat(s, nullptr, true);
+}
+extern "C" int hg_step(hg_handle s, hg_step_stats* stats) {   // hydro2d.hpp:1531-1621
+  if (!s) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  const size_t tdepth = s->timer_stack.size();
+  tpush(s, "step");
+  s->sweeps_total = 0; s->nsolves = 0;
+  // the device is waited for where the control flow needs a result (stop tests with a tolerance, dt_auto) and once at the
+  // end: NaN flags, solver status words, sweep counts and statistics come back in one block
+  s->defer = true;
+  CK(cudaMemsetAsync(s->flag + 4, 0, NF_COUNT * sizeof(int), s->st));
+  int nadv = 0;
+  int rc = step_body(s, &nadv);
+  s->defer = false;
+  while (s->timer_stack.size() > tdepth) tpop(s);   // also on error paths
+  if (rc) return rc;
+  const double* sb = s->hscal + ST_STATUS;
+  if (sb[8] != 0.) { s->err = "k_gs_tiled: dependency wait timed out"; return HG_ERR_CUDA; }
+  if (sb[9] != 0.) { s->err = "k_lu_tiled: dependency wait timed out"; return HG_ERR_CUDA; }
+  for (int q = 0; q < NF_COUNT; ++q) if (sb[q] != 0.) { s->err = nan_msgs[q]; return HG_ERR_NAN; }
+  s->sweeps_total += (int)sb[11];
+  if (s->nsolves > 0) s->last_diff = sb[12];
   s->stat.simple_iterations = s->iter_count;
-  double r = 1.; if (s->iter_count > 0) hg_fluid_convergence_indicator(s, &r);
-  s->stat.convergence_indicator = r;
+  if (s->iter_count > 0) s->last_resid = sb[10];
+  s->stat.convergence_indicator = s->iter_count > 0 ? sb[10] : 1.;
   s->stat.pressure_sweeps_total = s->sweeps_total;
   s->stat.pressure_last_diff = s->last_diff;
   s->stat.advection_substeps = nadv;
@@ -1084,6 +1185,11 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
   if (cfg->sharp != 0.) return fail_create(nullptr, HG_ERR_INVALID, "sharp != 0 is not on the GPU path");
   for (int sd = 0; sd < 2 * cfg->dim; ++sd)
     if (cfg->condition_kind[sd] == HG_BC_OUTLET) return fail_create(nullptr, HG_ERR_INVALID, "outlet conditions are not on the GPU path");
+  for (int id : {cfg->linear_solver_velocity, cfg->linear_solver_pressure, cfg->linear_solver_heat})
+    if (id < HG_LS_LU || id > HG_LS_JACOBI) return fail_create(nullptr, HG_ERR_INVALID, "Unknown linear solver");
+  if (cfg->linear_solver_velocity != HG_LS_LU) return fail_create(nullptr, HG_ERR_INVALID, "linear_solver_velocity: only lu runs on the GPU path");
+  if (cfg->heat_enable && cfg->linear_solver_heat != HG_LS_LU) return fail_create(nullptr, HG_ERR_INVALID, "linear_solver_heat: only lu runs on the GPU path");
+  if (cfg->linear_solver_pressure == HG_LS_LU) return fail_create(nullptr, HG_ERR_INVALID, "linear_solver_pressure: lu is not iterated for the pressure system on the GPU path");
   if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size || cfg->world_size > 64)
     return fail_create(nullptr, HG_ERR_INVALID, "bad world_size / rank");
   if (cfg->world_size > 1 && (cfg->dim != 3 || cfg->Nz < 2 * cfg->world_size))
@@ -1169,20 +1275,18 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     auto take_padded = [&](long long n) -> double* { double* q = take(n + 2 * padn); return q ? q + padn : nullptr; };
     T.D = take_padded(s->nsh); T.CYs = take_padded(s->nsh); T.CZs = take(dim > 2 ? s->nsh : 1); T.RP = take(s->nsh);
     T.PP = take_padded(s->nsh); T.PPsave = take(s->nsh);
-    T.scal = take(64); T.resid = take(4096);
-    // pressure sweeps: time-skewed tiles in 3-D on one GPU (HYDRO_GS_KERNEL=hyperplane keeps the pipelined
-    // hyperplane kernel, which is also what 2-D and the slab-decomposed runs use)
+    T.scal = take(64); T.resid = take(4096); T.sorres = take(2 * 4096);
+    // pressure sweeps: the box dataflow (k_gs_tiled) in 3-D, on one GPU and on every z-slab of a decomposed run;
+    // HYDRO_GS_KERNEL=hyperplane / HYDRO_GS_SLAB_KERNEL=hyperplane keep the pipelined hyperplane kernel (also used in 2-D)
     { const char* e = getenv("HYDRO_GS_KERNEL");
       const char* es = getenv("HYDRO_GS_SLAB_KERNEL");
-      // slabs: the box dataflow with tagged interface values is verified bit for bit for two slabs; with three or more it
-      // is opt-in (HYDRO_GS_SLAB_KERNEL=tiled): a 3-rank run with several sweep groups still times out on a shared device
-      const bool slab_ok = s->world == 1 || (s->world == 2 && !(es && !strcmp(es, "hyperplane"))) || (es && !strcmp(es, "tiled"));
+      const bool slab_ok = s->world == 1 || !(es && !strcmp(es, "hyperplane"));
       T.gs_tiled = dim == 3 && slab_ok && cfg->linear_solver_pressure == HG_LS_GAUSS_SEIDEL && !(e && !strcmp(e, "hyperplane")) &&
                    8LL * (GT_PAD + 2) * s->nxy < (1LL << 31);   // 32-bit byte offsets inside k_gs_tiled
     }
     if (T.gs_tiled) {
-      T.co_n = (long long)(s->geo.np + 2 * GT_PAD) * s->nxy;
-      T.DGs = take(s->nsh); T.CO = (double2*)take(4 * T.co_n * 2);
+      T.co5 = gt_co5(s->n[0], s->n[1], s->geo.np);
+      T.CO = take(5 * T.co5.arr);   // zeroed
     }
     // buffers peers read or write: exchange staging (2 parities x 2 directions x SLAB_MAX_ARRAYS x HG_HALO planes),
     // mailbox (2 parities x world x SLAB_MAIL doubles) and flag words
@@ -1194,9 +1298,10 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     if (!okA) return fail_create(s, HG_ERR_CUDA, "allocation failed: " + s->err);
   }
   bool ok = true;
-  if (ok) { int* fp = nullptr; ok = dalloc(s, &fp, 4) == 0; s->flag = fp; }
+  if (ok) { int* fp = nullptr; ok = dalloc(s, &fp, 16) == 0; s->flag = fp; }
   if (ok) { unsigned char* ep = nullptr; ok = dalloc(s, &ep, s->nxy * (s->n[2] + 2 * HG_HALO)) == 0; s->excl = ep ? ep + HG_HALO * s->nxy : nullptr; }
-  if (!ok || cudaMallocHost((void**)&s->hscal, 64 * 128 * sizeof(double)) != cudaSuccess) return fail_create(s, HG_ERR_CUDA, "allocation failed: " + s->err);
+  if (!ok || cudaMallocHost((void**)&s->hscal, 64 * 128 * sizeof(double)) != cudaSuccess ||
+      cudaMallocHost((void**)&s->hinit, 64 * sizeof(double)) != cudaSuccess) return fail_create(s, HG_ERR_CUDA, "allocation failed: " + s->err);
   // unused component slots alias a zero array so structs of 3 pointers are always valid
   for (int d = dim; d < 3; ++d) {
     for (int l = 0; l < 4; ++l) s->u[l][d] = nullptr;
@@ -1210,21 +1315,22 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
   s->num_sms = prop.multiProcessorCount;
   if (s->gs_tiled) {
     if (dalloc(s, &s->gt_ctl, 4, true)) return fail_create(s, HG_ERR_CUDA, "allocation failed: " + s->err);
-    // entry 0 of the sheared arrays (unused corner of the lower halo plane) is what threads without a cell read:
-    // zero coefficients (set by the allocation), unit diagonal
-    k_gt_co_fill<<<nblk(s->co_n), 256, 0, s->st>>>(s->CO, s->co_n);
+    // entries of the row arrays without a cell: zero coefficients (set by the allocation), unit diagonal
+    k_gt_co_fill<<<nblk(s->co5.arr), 256, 0, s->st>>>(s->CO + s->co5.arr, s->co5.arr);
     if (cudaStreamSynchronize(s->st) != cudaSuccess) return fail_create(s, HG_ERR_CUDA, "k_gt_co_fill failed");
-    { // TMA descriptor of the packed rows: doubles [4][np + 2 GT_PAD][ny][2 nx], box = the rows of 32 cells
+    if (gt_plans_allocate(s)) return fail_create(s, HG_ERR_CUDA, "allocation failed: " + s->err);
+    if (getenv("HYDRO_GT_CLOCK")) { if (dalloc(s, &s->gt_clk, 16, true)) return fail_create(s, HG_ERR_CUDA, "allocation failed: " + s->err); }
+    { // TMA descriptor of the row arrays: doubles [5][nhp][ny][nxp], box = one hyperplane under the footprint of a task
       typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
       void* fn = nullptr; cudaDriverEntryPointQueryResult qr;
       if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn)
         return fail_create(s, HG_ERR_CUDA, "cuTensorMapEncodeTiled not available");
-      const cuuint64_t nxd = 2ull * s->n[0], nyd = (cuuint64_t)s->n[1], npd = (cuuint64_t)(s->geo.np + 2 * GT_PAD);
-      const cuuint64_t dims[4] = {nxd, nyd, npd, 4};
-      const cuuint64_t strides[3] = {nxd * 8, nxd * 8 * nyd, nxd * 8 * nyd * npd};
-      const cuuint32_t box[4] = {64, 1, 1, 4}, estr[4] = {1, 1, 1, 1};
+      const Co5& co = s->co5;
+      const cuuint64_t dims[4] = {(cuuint64_t)s->n[0], (cuuint64_t)s->n[1], (cuuint64_t)co.nhp, 5};
+      const cuuint64_t strides[3] = {(cuuint64_t)co.nxp * 8, (cuuint64_t)co.plane * 8, (cuuint64_t)co.arr * 8};
+      const cuuint32_t box[4] = {GT_CW, GT_CH, 1, 5}, estr[4] = {1, 1, 1, 1};
       const CUresult r = ((EncodeFn)fn)(&s->tmco, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, s->CO, dims, strides, box, estr,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1427,6 +1533,11 @@ extern "C" int hg_destroy(hg_handle s) {
   for (void* p : s->allocs) cudaFree(p);
   if (s->hscal) cudaFreeHost(s->hscal);
   if (s->hdiffs) cudaFreeHost(s->hdiffs);
+  if (s->hinit) cudaFreeHost(s->hinit);
+  for (auto& pl : s->gt_plans) { if (pl.stage) cudaFreeHost(pl.stage); if (pl.staged) cudaEventDestroy(pl.staged); }
+  for (cudaEvent_t e : s->user_ev) if (e) cudaEventDestroy(e);
+  for (auto& v : s->prof_ev) for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  if (s->xfer_ev_tmp[0]) { cudaEventDestroy(s->xfer_ev_tmp[0]); cudaEventDestroy(s->xfer_ev_tmp[1]); }
   for (auto& kv : s->timers) { if (kv.second.a) { cudaEventDestroy(kv.second.a); cudaEventDestroy(kv.second.b); } }
   cudaStreamDestroy(s->st);
   if (s->st_h2d) cudaStreamDestroy(s->st_h2d);
@@ -1440,6 +1551,17 @@ extern "C" const char* hg_last_error(hg_handle s) { return s ? s->err.c_str() : 
 extern "C" size_t hg_num_cells(hg_handle s) { return s ? (size_t)s->nc : 0; }
 extern "C" size_t hg_num_faces(hg_handle s) { return s ? (size_t)s->nf : 0; }
 extern "C" long long hg_launch_count(hg_handle s) { return s ? s->launches : 0; }
+extern "C" const char* hg_solver_kernel_name(hg_handle s, int which) {
+  if (!s) return "";
+  if (which == 0) {
+    if (s->cfg.linear_solver_pressure == HG_LS_JACOBI) return "k_jacobi_sweep";
+    if (s->cfg.linear_solver_pressure == HG_LS_LU_RELAXED) return "k_lur_forward";
+    if (s->gs_tiled) return s->world > 1 ? "k_gs_tiled<LINK>" : "k_gs_tiled";
+    return s->world > 1 ? "k_gs_persistent<LINK>" : "k_gs_persistent";
+  }
+  if (s->lu_tiled) return s->world > 1 ? "k_lu_tiled<LINK>" : "k_lu_tiled";
+  return s->world > 1 ? "k_lu_persistent<LINK>" : "k_lu_persistent";
+}
 extern "C" int hg_device_synchronize(hg_handle s) {
   if (!s) return HG_ERR_INVALID;
   cudaSetDevice(s->dev);
@@ -1493,6 +1615,8 @@ static int xfer_setup(hg_state* s, int field, long long m, std::map<int, double*
   if (!s->st_h2d) {
     CK(cudaStreamCreateWithFlags(&s->st_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&s->st_d2h, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&s->xfer_ev_tmp[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s->xfer_ev_tmp[1], cudaEventDisableTiming));
   }
   auto it = bufs.find(field);
   if (it == bufs.end()) {
@@ -1510,12 +1634,10 @@ extern "C" int hg_set_field_async(hg_handle s, int field, const double* src, siz
   if (!p || (long long)n != m || field == HG_F_EXCLUDED) { s->err = "hg_set_field_async: bad field id or size"; return HG_ERR_INVALID; }
   double* stage = nullptr;
   if (int rc = xfer_setup(s, field, m, s->xfer_stage, &stage)) return rc;
-  cudaEvent_t ev = nullptr;
-  CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  CK(cudaEventRecord(ev, s->st)); CK(cudaStreamWaitEvent(s->st_h2d, ev, 0));   // the staging buffer's last consumer is done
+  // (an event can be re-recorded once the wait on its previous record has been enqueued)
+  CK(cudaEventRecord(s->xfer_ev_tmp[0], s->st)); CK(cudaStreamWaitEvent(s->st_h2d, s->xfer_ev_tmp[0], 0));   // the staging buffer's last consumer is done
   CK(cudaMemcpyAsync(stage, src, n * sizeof(double), cudaMemcpyHostToDevice, s->st_h2d));
-  CK(cudaEventRecord(ev, s->st_h2d)); CK(cudaStreamWaitEvent(s->st, ev, 0));
-  CK(cudaEventDestroy(ev));
+  CK(cudaEventRecord(s->xfer_ev_tmp[1], s->st_h2d)); CK(cudaStreamWaitEvent(s->st, s->xfer_ev_tmp[1], 0));
   CK(cudaMemcpyAsync(p, stage, n * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
   if (field <= HG_F_TEMPERATURE) {
     double* q = field_ptr(s, field, L_TP, &m);
@@ -1538,10 +1660,7 @@ extern "C" int hg_get_field_async(hg_handle s, int field, double* dst, size_t n)
     CK(cudaStreamWaitEvent(s->st, it->second, 0));   // the previous download of this snapshot has finished
   }
   CK(cudaMemcpyAsync(snap, p, n * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
-  cudaEvent_t ev = nullptr;
-  CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  CK(cudaEventRecord(ev, s->st)); CK(cudaStreamWaitEvent(s->st_d2h, ev, 0));
-  CK(cudaEventDestroy(ev));
+  CK(cudaEventRecord(s->xfer_ev_tmp[0], s->st)); CK(cudaStreamWaitEvent(s->st_d2h, s->xfer_ev_tmp[0], 0));
   CK(cudaMemcpyAsync(dst, snap, n * sizeof(double), cudaMemcpyDeviceToHost, s->st_d2h));
   CK(cudaEventRecord(it->second, s->st_d2h));
   return 0;
@@ -1614,6 +1733,7 @@ extern "C" int hg_linear_solve(hg_handle s, int solver, const double* const coef
   int it = 0; double df = 0.;
   if (solver == HG_LS_LU) {
     if (int rc = solve_lu(s, 1)) return rc;
+    if (s->lu_tiled) if (int rc = lt_check(s)) return rc;
     DIMSEL(s, k_from_sheared, gb, 256, s->geo, s->X[0], s->pc);
   } else if (solver == HG_LS_GAUSS_SEIDEL) {
     auto launch = [&](int sb, int se) -> int {
@@ -1692,6 +1812,17 @@ extern "C" int hg_profile_read(hg_handle s, int which, int* count, double* total
   }
   s->prof_ev[which].clear();
   *count = n; *total_ms = tot;
+  return 0;
+}
+
+extern "C" int hg_profile_read_clocks(hg_handle s, unsigned long long out[16]) {
+  if (!s || !out) return HG_ERR_INVALID;
+  cudaSetDevice(s->dev);
+  for (int q = 0; q < 16; ++q) out[q] = 0;
+  if (!s->gt_clk) return 0;
+  CK(cudaMemcpyAsync(out, s->gt_clk, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->st));
+  CK(cudaMemsetAsync(s->gt_clk, 0, 16 * sizeof(unsigned long long), s->st));
+  CK(cudaStreamSynchronize(s->st));
   return 0;
 }
 

@@ -92,6 +92,15 @@ class hydro_gpu : public TModule {
     c.density_smooth_times = P_int["density_smooth_times"]; c.viscosity_smooth_times = P_int["viscosity_smooth_times"];
     c.force_smooth_times = P_int["force_smooth_times"];
     if (P_string["advection_solver"] != "tvd") throw std::runtime_error("hydro_gpu: only advection_solver tvd");
+    // options that change the reference's results and are not on the GPU path fail loudly (never silently dropped)
+    for (const char* k : {"compressible_enable", "deforming_velocity", "radiation_enable"})
+      if (flag(k)) throw std::runtime_error(std::string("hydro_gpu: ") + k + " 1 is not on the GPU path");
+    if ((P_string.exist("chemistry") && P_string["chemistry"] != "steady") || (P_double.exist("chem_intensity") && P_double["chem_intensity"] != 0.))
+      throw std::runtime_error("hydro_gpu: chemistry other than 'steady' with chem_intensity 0 is not on the GPU path");
+    for (const char* k : {"meshvel_auto", "imgu_init", "imgv_init", "img_init"})
+      if (P_string.exist(k)) throw std::runtime_error(std::string("hydro_gpu: ") + k + " is not on the GPU path");
+    for (int i = 0; i < c.num_phases; ++i)
+      if (flag("enable_settling_" + IntToStr(i))) throw std::runtime_error("hydro_gpu: phase slip (enable_settling) is not on the GPU path");
     c.advection_dt_factor = P_double["advection_dt_factor"]; c.tvd_split = P_bool["tvd_split"]; c.sharp = P_double["sharp"];
     c.heat_enable = P_bool["heat_enable"]; c.temperature_initial = P_double["temperature_initial"];
     vec("heat_box_lb", c.heat_box_lb); vec("heat_box_rt", c.heat_box_rt);
@@ -116,7 +125,7 @@ class hydro_gpu : public TModule {
     P_int.set("s_sum", 0); P_int.set("s_max", 0); P_int.set("s", 0);
     h_.Create(config());                       // throws std::string on failure, like the reference
     P_int.set("cells_number", static_cast<int>(h_.NumCells()));
-    h_.Check(hg_calc_stat(h_.get(), &st_));
+    h_.Check(hg_get_stats(h_.get(), &st_));   // the CalcStat of the constructor (hydro2d.hpp:962) ran inside hg_create
     publish_stat();
   }
   void step() override {

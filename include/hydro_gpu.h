@@ -59,7 +59,7 @@ enum hg_status {
   HG_ERR_NO_DEVICE = -2,   /* no CUDA device: there is no CPU fallback  */
   HG_ERR_CUDA = -3,        /* CUDA runtime error                        */
   HG_ERR_NAN = -4,         /* reference: throw std::string("NaN ...")   */
-  HG_ERR_NCCL = -5
+  HG_ERR_PEER = -5         /* slab decomposition: a wait for a neighbouring rank timed out */
 };
 
 /* Field ids for hg_set_field / hg_get_field.  Cell fields have n = nx*ny*nz
@@ -136,10 +136,10 @@ typedef struct hg_config {
   double heat_box_lb[3], heat_box_rt[3], heat_box_temperature, heat_relaxation_factor;
   int time_second_order_heat;
   /* multi-GPU z-slab decomposition (no reference counterpart: its MPI is a stub,
-   * source/main.cpp:26-28).  world_size 1 = single GPU.  For world_size > 1 the
-   * caller provides the NCCL unique id bytes (128) shared by all ranks. */
+   * source/main.cpp:26-28).  world_size 1 = single GPU.  For world_size > 1 the ranks
+   * are linked after hg_create with hg_ipc_export/hg_ipc_import (one process per GPU)
+   * or hg_link_local (one process); the data plane is NVLink peer memory. */
   int world_size, rank, device;
-  const void* nccl_unique_id;
   /* execution options */
   int pressure_sweeps_per_check;   /* 0 = default */
   int solver_ctas;                 /* 0 = one CTA per SM; >0 limits the persistent solver grids (ranks sharing a device) */
@@ -199,7 +199,10 @@ int hg_get_field_async(hg_handle h, int field, double* dst, size_t n);
 
 /* one whole time step = hydro<Mesh>::step() (hydro2d.hpp:1531-1621) */
 int hg_step(hg_handle h, hg_step_stats* stats /* may be NULL */);
-/* n steps back to back without host synchronisation in between */
+/* n steps back to back.  The host only waits for the device where the reference's control flow depends on
+ * device results: once per step (NaN flags, solver status words, statistics, all in one pinned status block),
+ * plus once per SIMPLE iteration when convergence_tolerance > 0 and once per chunk of pressure sweeps when
+ * lu_relaxed_tolerance > 0 (the stop tests of solver.hpp:733-736 and linear.hpp:707-710). */
 int hg_run(hg_handle h, int nsteps, hg_step_stats* last_stats /* may be NULL */);
 
 /* fine-grained protocol = solver::UnsteadyIterativeSolver (solver.hpp:710-751)
@@ -217,7 +220,8 @@ int hg_set_time_step(hg_handle h, double dt_fluid, double dt_advection);
 int hg_advection_step(hg_handle h);                          /* Start/CalcStep/Finish, advection.hpp:417-545 */
 int hg_heat_step(hg_handle h);                               /* heat.hpp:69-84 */
 int hg_update_properties(hg_handle h);                       /* hydro2d.hpp:1404-1430 */
-int hg_calc_stat(hg_handle h, hg_step_stats* stats);         /* hydro2d.hpp:1432-1529 */
+int hg_calc_stat(hg_handle h, hg_step_stats* stats);         /* hydro2d.hpp:1432-1529, incl. meshpos += meshvel*dt (1526-1528) */
+int hg_get_stats(hg_handle h, hg_step_stats* stats);         /* the statistics of the last CalcStat, nothing is recomputed or advanced */
 
 /* kernel-level entries (parity tests and micro-benchmarks, cf. test/benchmark/main.cpp) */
 
@@ -246,6 +250,8 @@ int hg_timers_enable(hg_handle h, int enable);
 
 /* counts kernels launched by this handle since creation (bench.py "gpu_launches") */
 long long hg_launch_count(hg_handle h);
+/* name of the kernel the handle runs for (which: 0 = pressure sweeps, 1 = lu); bench.py labels its roofline with it */
+const char* hg_solver_kernel_name(hg_handle h, int which);
 
 /* device/bench helpers: CUDA events recorded on the handle's own stream (8 slots), and per-launch
  * timing of the two persistent solver kernels (which: 0 = pressure sweeps, 1 = lu); reading clears */
@@ -254,6 +260,8 @@ int hg_event_elapsed_ms(hg_handle h, int slot_a, int slot_b, double* ms);
 int hg_profile_enable(hg_handle h, int enable);
 int hg_profile_read(hg_handle h, int which, int* count, double* total_ms);
 int hg_device_synchronize(hg_handle h);
+/* cycle counters of the sweep kernel's warp roles (only in builds with -DGT_CLOCK and HYDRO_GT_CLOCK=1; zeros otherwise); reading clears */
+int hg_profile_read_clocks(hg_handle h, unsigned long long out[16]);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,8 @@ def lib(fast=False):
     name = "liboracle_fast.so" if fast else "liboracle.so"
     path = os.path.join(ORACLE_DIR, name)
     src = os.path.join(ORACLE_DIR, "hydro_oracle.c")
-    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+    hdr = os.path.join(os.path.dirname(ORACLE_DIR), "include", "hydro_gpu.h")
+    if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
         subprocess.check_call(["make", "-C", ORACLE_DIR, name], stdout=subprocess.DEVNULL)
     if fast:
         return _bind(C.CDLL(path))

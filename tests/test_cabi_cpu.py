@@ -95,3 +95,16 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+\S*oracle|liboracle|#include\s+\"[^\"]*oracle|dlopen", txt, re.M), f
+
+
+@pytest.mark.parametrize("key,val", [("compressible_enable", 1), ("deforming_velocity", 1), ("radiation_enable", 1),
+                                     ("chemistry", "Nadirov"), ("chem_intensity", 0.5), ("meshvel_auto", "phase0"),
+                                     ("imgu_init", "u.pgm"), ("enable_settling_1", 1)])
+def test_options_outside_the_gpu_path_are_rejected(key, val):
+    """Options that change the reference's results (hydro2d.hpp:326-368, 1030-1217, 1294, 1387, 1511-1524) must not be
+    dropped silently: Params.to_struct raises before a handle is created."""
+    import cases
+    p = cases.rt3d(8)
+    p[key] = val
+    with pytest.raises(ValueError, match="GPU path"):
+        p.to_struct()

@@ -15,6 +15,7 @@ import cases
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 BIN = os.path.join(ROOT, "hydro_b200", "host", "_build", "hydro_gpu")
+SHIM = os.path.join(ROOT, "hydro_b200", "host", "_build", "shim_check")
 
 
 def run_console(params, nsteps):
@@ -35,8 +36,7 @@ def run_console(params, nsteps):
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", ["rt3d", "cavity"])
 def test_same_script_cpu_module_vs_gpu_module(case):
-    if not os.access(BIN, os.X_OK):
-        pytest.skip("hydro_b200/host/_build/hydro_gpu not built (needs /root/reference at build time)")
+    assert os.access(BIN, os.X_OK), "hydro_b200/host/_build/hydro_gpu not built: __graft_entry__.build() makes it where /root/reference exists"
     if case == "rt3d":
         p, mods, nsteps = cases.rt3d(16), ("hydro3d", "hydro3d_gpu"), 3
     else:
@@ -47,3 +47,39 @@ def test_same_script_cpu_module_vs_gpu_module(case):
         rs, log = run_console(p, nsteps)
         out.append(rs)
     assert len(out[0]) >= nsteps and out[0] == out[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["rt3d", "dam3d"])
+def test_solver_shim_protocol_equals_hg_step(case):
+    """Secondary boundary (SURVEY 8b): hydro_b200/host/hydro_gpu.hpp mirrors solver::FluidSolver (fluid.hpp:202-253) and
+    AdvectionSolverMulti (advection.hpp:62-84).  A C++ host program drives StartStep / IsConverged / MakeIteration /
+    FinishStep / advection / properties / statistics the way hydro<Mesh>::step() does and dumps the getters' host mirrors;
+    the fields must equal hg_step() on the same configuration bit for bit."""
+    import numpy as np
+    from hydro_b200.capi import Hydro
+    assert os.access(SHIM, os.X_OK), "hydro_b200/host/_build/shim_check not built (make -C hydro_b200/host shim)"
+    p = cases.rt3d(12) if case == "rt3d" else cases.broken_dam_3d(32, 10, 10, lu_relaxed_num_iters_limit=40, advection_dt_factor=1.0)
+    nsteps = 2
+    h = Hydro(p)
+    for _ in range(nsteps):
+        st = h.step()
+    names = ["VELOCITY_X", "VELOCITY_Y", "VELOCITY_Z", "PRESSURE", "VOLUME_FLUX", "PARTIAL_DENSITY_0", "PARTIAL_DENSITY_1"]
+    want = [h.get(n) for n in names]
+    with tempfile.TemporaryDirectory() as tmp:
+        with open(os.path.join(tmp, "cfg.bin"), "wb") as f:
+            f.write(bytes(h.cfg))
+        r = subprocess.run([SHIM, os.path.join(tmp, "cfg.bin"), str(nsteps), os.path.join(tmp, "out.bin")],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-800:]
+        raw = open(os.path.join(tmp, "out.bin"), "rb").read()
+    got, off = [], 0
+    while off < len(raw):
+        n = int(np.frombuffer(raw, dtype=np.uint64, count=1, offset=off)[0])
+        got.append(np.frombuffer(raw, dtype=np.float64, count=n, offset=off + 8))
+        off += 8 + 8 * n
+    assert len(got) == len(want)
+    for n, a, b in zip(names, got, want):
+        assert np.array_equal(a, b), n
+    m = re.search(r"indicator (\S+)", r.stdout)
+    assert float(m.group(1)) == st.convergence_indicator

@@ -151,6 +151,35 @@ def test_gpu_rt3d_medium(n):
     run_both(cases.rt3d(n), 2)
 
 
+def test_gpu_rt3d_128_against_fast_oracle():
+    """W4 at 128^3 (2.1 M cells, fixed work): the largest size the C restatement finishes in about ten seconds per
+    step (liboracle_fast.so, -O3).  Same bound as the small cases: 1e-12 relative L2 per field, equal SIMPLE-iteration
+    and sweep counts.  Covers the index arithmetic of every kernel at a size where the box dataflow runs many boxes per
+    SM and several sweep groups (the 256^3 test below can only compare two GPU schedules with each other)."""
+    from hydro_b200.capi import Hydro
+    p = cases.rt3d(128)
+    gpu, cpu = Hydro(p), Oracle(p, fast=True)
+    sg, sc = gpu.step(), cpu.step()
+    assert sg.simple_iterations == sc.simple_iterations == 3
+    assert sg.pressure_sweeps_total == sc.pressure_sweeps_total
+    np.testing.assert_allclose(gpu.residuals(), cpu.residuals(), rtol=1e-9)
+    np.testing.assert_allclose(sg.pressure_last_diff, sc.pressure_last_diff, rtol=1e-8)
+    compare_states(gpu, cpu, TOL)
+
+
+def test_get_stats_does_not_advance_the_mesh_position():
+    """CalcStat adds meshvel*dt to the mesh position (hydro2d.hpp:1526-1528) once per call: hg_calc_stat keeps that,
+    hg_get_stats only returns the last statistics (the module constructor uses it)."""
+    from hydro_b200.capi import Hydro
+    p = cases.cavity(12, meshvel=(0.25, 0, 0), num_phases=1)
+    gpu, cpu = Hydro(p), Oracle(p)
+    a, b = gpu.get_stats(), gpu.get_stats()
+    assert a.center[0][0] == b.center[0][0]
+    sg, sc = gpu.step(), cpu.step()
+    np.testing.assert_allclose(sg.center[0][0], sc.center[0][0], rtol=1e-12)
+    assert gpu.get_stats().center[0][0] == sg.center[0][0]
+
+
 def test_gpu_dam3d_as_shipped():
     """examples/broken_dam_3d as shipped (64x20x20, obstacle)."""
     run_both(cases.broken_dam_3d(64, 20, 20, lu_relaxed_num_iters_limit=60), 2)
@@ -283,6 +312,8 @@ def test_error_convention():
         Hydro(cases.cavity(8, simpler=1))
     with pytest.raises(RuntimeError, match="outlet"):
         Hydro(cases.cavity(8, condition_right="outlet"))
+    with pytest.raises(RuntimeError, match="linear_solver_velocity"):
+        Hydro(cases.cavity(8, linear_solver_velocity="jacobi"))
     h = Hydro(cases.cavity(8))
     with pytest.raises(RuntimeError, match="bad field"):
         h.set("PRESSURE", np.zeros(3))
