@@ -463,8 +463,15 @@ static int gt_build_tasks(hg_state* s, int S, GtTask* tasks, int* ntasks) {
     const int nsw = nsw_of(gI);
     return I * GT_TX - (nsw - 1) < nx && J * GT_TY - (nsw - 1) < ny;
   };
-  for (int gI = 0; gI < NG; ++gI) for (int J = 0; J < NJ; ++J) for (int I = 0; I < NI; ++I)
-    if (exists(I, J, gI)) keys.push_back({GT_TX * I + GT_TY * J + (GT_TX + GT_TY + 2 * GT_B + 2) * gI, gI, J, I});
+  // Claim order: by a weighted start step WI I + WJ J + WG group.  The natural weights (TX, TY, TX + TY + 2B + 2) claim the
+  // boxes in the order in which they can start.  Any weights with WG > WI + WJ put every dependency of a box before it.
+  // A smaller WJ brings the boxes (I, J) and (I, J+1), whose (TY + B)-row footprints share B rows, closer together in
+  // time, so that the shared rows are still in L2 when the second box asks for them.
+  static const int WJ = getenv("HYDRO_GT_WJ") ? std::max(0, atoi(getenv("HYDRO_GT_WJ"))) : GT_TY;
+  static const int WI = getenv("HYDRO_GT_WI") ? std::max(1, atoi(getenv("HYDRO_GT_WI"))) : GT_TX;
+  const int WG = WI + WJ + 2 * GT_B + 2;
+  for (int gI = 0; gI < NG; ++gI) for (int I = 0; I < NI; ++I) for (int J = 0; J < NJ; ++J)
+    if (exists(I, J, gI)) keys.push_back({WI * I + WJ * J + WG * gI, gI, J, I});
   std::stable_sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.w < b.w; });
   std::vector<int> index((size_t)NG * NJ * NI, -1);
   auto at = [&](int I, int J, int gI) -> int { return exists(I, J, gI) ? index[((size_t)gI * NJ + J) * NI + I] : -1; };
