@@ -626,17 +626,17 @@ static int solve_lu_tiled(hg_state* s, int ncomp) {
   a.link = slab_link(s, 1); a.link_stride = s->nxy;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (s->profile_on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s->st); }
-  int grid = std::min(s->lt_nboxes, s->num_sms * std::max(1, 512 / LT_THREADS));   // all boxes resident when they fit
+  int grid = std::min(s->lt_nboxes, s->num_sms * LT_CTAS_PER_SM);   // all boxes resident when they fit
   if (s->cfg.solver_ctas > 0) grid = std::min(grid, s->cfg.solver_ctas);           // ranks sharing a device (tests)
   for (int dir = 0; dir < 2; ++dir) {
     CK(cudaMemsetAsync(s->lt_progress, 0, s->lt_nboxes * sizeof(int), s->st));
     CK(cudaMemsetAsync(s->lt_ctl, 0, sizeof(int), s->st));   // next-box counter; the abort flag [1] is sticky
     if (s->world > 1) {
-      if (dir == 0) k_lu_tiled<0, true><<<grid, LT_THREADS, 0, s->st>>>(s->geo, a);
-      else k_lu_tiled<1, true><<<grid, LT_THREADS, 0, s->st>>>(s->geo, a);
+      if (dir == 0) k_lu_tiled<0, true><<<grid, LT_THREADS, LT_RING_BYTES, s->st>>>(s->geo, a);
+      else k_lu_tiled<1, true><<<grid, LT_THREADS, LT_RING_BYTES, s->st>>>(s->geo, a);
     } else {
-      if (dir == 0) k_lu_tiled<0><<<grid, LT_THREADS, 0, s->st>>>(s->geo, a);
-      else k_lu_tiled<1><<<grid, LT_THREADS, 0, s->st>>>(s->geo, a);
+      if (dir == 0) k_lu_tiled<0><<<grid, LT_THREADS, LT_RING_BYTES, s->st>>>(s->geo, a);
+      else k_lu_tiled<1><<<grid, LT_THREADS, LT_RING_BYTES, s->st>>>(s->geo, a);
     }
     CK(cudaGetLastError());
     ++s->launches;
@@ -1349,6 +1349,11 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
   { const char* e = getenv("HYDRO_LU_KERNEL");
     s->lu_tiled = dim == 3 && !(e && !strcmp(e, "hyperplane")); }
   if (s->lu_tiled) {
+    if (cudaFuncSetAttribute(k_lu_tiled<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_RING_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_lu_tiled<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_RING_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_lu_tiled<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_RING_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_lu_tiled<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_RING_BYTES) != cudaSuccess)
+      return fail_create(s, HG_ERR_CUDA, "k_lu_tiled: shared memory request rejected");
     const int nbi = (s->n[0] + LT_TX - 1) / LT_TX, nbj = (s->n[1] + LT_TY - 1) / LT_TY;
     std::vector<int2> boxes;
     for (int J = 0; J < nbj; ++J) for (int I = 0; I < nbi; ++I) boxes.push_back(make_int2(I, J));
