@@ -16,6 +16,7 @@ namespace cg = cooperative_groups;
 #define CELL_LOOP_PROLOG(g)                                                   \
   long long c_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;            \
   long long nc_ = (long long)(g).n[0] * (g).n[1] * (g).n[2];                  \
+  if ((g).cells) { if (c_ >= (g).ncells) return; c_ = (g).cells[c_]; }        \
   if (c_ >= nc_) return;                                                      \
   int i, j, k;                                                                \
   if (nc_ < (1LL << 31)) {                                                    \
@@ -431,44 +432,39 @@ DV double face_coeff(const Geo& g, const double* __restrict__ dc, int d, const F
 
 // K_prhs: constants of the pressure-correction rows (fluid.hpp:972-1014) and the diagonal field in
 // the sheared layout; the sweep kernels regenerate the off-diagonals A/(h d_f) from it.
+// One cell of K_prhs: rp = constant, cf[d] = plus-face coefficients, dg = explicit diagonal (only when want_dg)
 template <int DIM>
-__global__ void __launch_bounds__(256, 6) k_prhs(Geo g, const double* __restrict__ Fs, const double* __restrict__ dc, int out_sheared,
-                       double* __restrict__ RP, double* __restrict__ CX, double* __restrict__ CY, double* __restrict__ CZ,
-                       double* __restrict__ DG = nullptr) {
-  CELL_LOOP_PROLOG(g)
-  const long long cs = out_sheared ? shidx(g, i, j, k) : c;
+DV void prhs_cell(const Geo& g, const double* __restrict__ Fs, const double* __restrict__ dc, int i, int j, int k, long long c,
+                  bool want_dg, double& rp, double (&cf)[3], double& dg) {
   // face coefficients of the cell's plus faces for the sweep kernel (0 when the face is not inner)
-  {
-    double cf[3] = {0., 0., 0.};
+  cf[0] = cf[1] = cf[2] = 0.; dg = 0.;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    FaceInfo f = face_info<DIM>(g, d, i + (d == 0), j + (d == 1), k + (d == 2));
+    if (f.type == FT_INNER) cf[d] = face_coeff<DIM>(g, dc, d, f);
+  }
+  if (want_dg) {
+    // k_gs_tiled: explicit diagonal = ordered sum over the faces x-,x+,y-,y+,z-,z+ (fluid.hpp:979-984; absent
+    // faces add 0), 1 for identity rows; the coefficients of the faces of the fixed-pressure cell are stored
+    // as 0 so that the terms removed by SetKnownValue (fluid.hpp:1010) vanish from the sums
+    double cm[3] = {0., 0., 0.};
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
-      FaceInfo f = face_info<DIM>(g, d, i + (d == 0), j + (d == 1), k + (d == 2));
-      if (f.type == FT_INNER) cf[d] = face_coeff<DIM>(g, dc, d, f);
+      FaceInfo f = face_info<DIM>(g, d, i, j, k);
+      if (f.type == FT_INNER) cm[d] = face_coeff<DIM>(g, dc, d, f);
     }
-    if (DG) {
-      // k_gs_tiled: explicit diagonal = ordered sum over the faces x-,x+,y-,y+,z-,z+ (fluid.hpp:979-984; absent
-      // faces add 0), 1 for identity rows; the coefficients of the faces of the fixed-pressure cell are stored
-      // as 0 so that the terms removed by SetKnownValue (fluid.hpp:1010) vanish from the sums
-      double cm[3] = {0., 0., 0.};
+    double diag = cm[0] + cf[0]; diag = diag + cm[1]; diag = diag + cf[1];
+    if (DIM > 2) { diag = diag + cm[2]; diag = diag + cf[2]; }
+    const bool ident = c == g.pfix || cell_excl(g, i, j, k);
+    dg = ident ? 1. : diag;
 #pragma unroll
-      for (int d = 0; d < DIM; ++d) {
-        FaceInfo f = face_info<DIM>(g, d, i, j, k);
-        if (f.type == FT_INNER) cm[d] = face_coeff<DIM>(g, dc, d, f);
-      }
-      double diag = cm[0] + cf[0]; diag = diag + cm[1]; diag = diag + cf[1];
-      if (DIM > 2) { diag = diag + cm[2]; diag = diag + cf[2]; }
-      const bool ident = c == g.pfix || cell_excl(g, i, j, k);
-      DG[cs] = ident ? 1. : diag;
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) {
-        const long long nb = cidx(g, i + (d == 0), j + (d == 1), k + (d == 2));
-        if (c == g.pfix || nb == g.pfix) cf[d] = 0.;
-      }
+    for (int d = 0; d < DIM; ++d) {
+      const long long nb = cidx(g, i + (d == 0), j + (d == 1), k + (d == 2));
+      if (c == g.pfix || nb == g.pfix) cf[d] = 0.;
     }
-    CX[cs] = cf[0]; CY[cs] = cf[1]; if (DIM > 2) CZ[cs] = cf[2];
   }
-  if (cell_excl(g, i, j, k)) { RP[cs] = 0.; return; }
-  if (c == g.pfix) { RP[cs] = -g.pfix_value; return; }
+  if (cell_excl(g, i, j, k)) { rp = 0.; return; }
+  if (c == g.pfix) { rp = -g.pfix_value; return; }
   double cst = 0.;
   double extra = 0.; bool has_extra = false;
 #pragma unroll
@@ -489,12 +485,23 @@ __global__ void __launch_bounds__(256, 6) k_prhs(Geo g, const double* __restrict
       const int fi = i + (d == 0 ? o : 0), fj = j + (d == 1 ? o : 0), fk = k + (d == 2 ? o : 0);
       FaceInfo f = face_info<DIM>(g, d, fi, fj, fk);
       if (f.type != FT_INNER) continue;
-      const double cf = face_coeff<DIM>(g, dc, d, f);
-      extra = g.pfix_value * (-cf); has_extra = true;
+      const double cfn = face_coeff<DIM>(g, dc, d, f);
+      extra = g.pfix_value * (-cfn); has_extra = true;
     }
   }
-  (void)has_extra;
-  RP[cs] = (g.pfix != HG_NO_CELL && has_extra) ? rhs + extra : rhs;
+  rp = (g.pfix != HG_NO_CELL && has_extra) ? rhs + extra : rhs;
+}
+template <int DIM>
+__global__ void __launch_bounds__(256, 6) k_prhs(Geo g, const double* __restrict__ Fs, const double* __restrict__ dc, int out_sheared,
+                       double* __restrict__ RP, double* __restrict__ CX, double* __restrict__ CY, double* __restrict__ CZ,
+                       double* __restrict__ DG = nullptr) {
+  CELL_LOOP_PROLOG(g)
+  const long long cs = out_sheared ? shidx(g, i, j, k) : c;
+  double rp, cf[3], dg;
+  prhs_cell<DIM>(g, Fs, dc, i, j, k, c, DG != nullptr, rp, cf, dg);
+  if (DG) DG[cs] = dg;
+  CX[cs] = cf[0]; CY[cs] = cf[1]; if (DIM > 2) CZ[cs] = cf[2];
+  RP[cs] = rp;
 }
 
 // K_prows: explicit rows of the pressure-correction system (fluid.hpp:972-1014) for solvers that need the
@@ -663,41 +670,72 @@ __global__ void __launch_bounds__(256, 8) k_advect(Geo g, const double* __restri
 // ---------------------------------------------------------------- statistics (CalcStat, hydro2d.hpp:1432-1466)
 // out[ph*12 + {0 volume, 1..3 centre sums, 4..6 velocity sums}] (atomicAdd), out[ph*12+7] pd_min, +8 pd_max
 struct StatArgs { int np; const double* vf[3]; const double* pd[3]; const double* u[3]; double* out; };
+constexpr int STAT_CPT = 8;   // cells per thread: partial sums in registers, one block reduction at the end
 template <int DIM>
-__global__ void __launch_bounds__(256, 6) k_stat(Geo g, StatArgs a) {
-  long long c_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long nc_ = (long long)g.n[0] * g.n[1] * g.n[2];
-  const bool ok = c_ < nc_;
-  int i = 0, j = 0, k = 0;
-  if (ok) { i = (int)(c_ % g.n[0]); j = (int)((c_ / g.n[0]) % g.n[1]); k = (int)(c_ / ((long long)g.n[0] * g.n[1])); }
-  double x[3]; cell_center(g, i, j, k, x);
-  __shared__ double sm[32];
-  for (int ph = 0; ph < a.np; ++ph) {
-    double vals[9];
-    const double cc = ok ? a.vf[ph][c_] : 0.;
-    const double w = cc * g.vol;
-    vals[0] = w;
-    for (int d = 0; d < 3; ++d) { vals[1 + d] = (ok && d < DIM) ? x[d] * w : 0.; vals[4 + d] = (ok && d < DIM) ? a.u[d][c_] * w : 0.; }
-    const double pd = ok ? a.pd[ph][c_] : 0.;
-    vals[7] = ok ? pd : 1e300; vals[8] = ok ? pd : -1e300;
-    for (int q = 0; q < 9; ++q) {
-      double v = vals[q];
-      if (q < 7) v = warp_sum(v); else if (q == 7) v = warp_min(v); else v = warp_max(v);
-      __syncthreads();
-      if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
-      __syncthreads();
-      if (threadIdx.x < 32) {
-        const int nw = blockDim.x >> 5;
-        if (q < 7) { v = threadIdx.x < nw ? sm[threadIdx.x] : 0.; v = warp_sum(v); if (threadIdx.x == 0) atomicAdd(&a.out[ph * 12 + q], v); }
-        else if (q == 7) { v = threadIdx.x < nw ? sm[threadIdx.x] : 1e300; v = warp_min(v);
-          if (threadIdx.x == 0) { // signed doubles: CAS loop
-            unsigned long long* ad = (unsigned long long*)&a.out[ph * 12 + 7]; unsigned long long old = *ad, assumed;
-            do { assumed = old; if (!(v < __longlong_as_double((long long)assumed))) break; old = atomicCAS(ad, assumed, (unsigned long long)__double_as_longlong(v)); } while (assumed != old); } }
-        else { v = threadIdx.x < nw ? sm[threadIdx.x] : -1e300; v = warp_max(v);
-          if (threadIdx.x == 0) {
-            unsigned long long* ad = (unsigned long long*)&a.out[ph * 12 + 8]; unsigned long long old = *ad, assumed;
-            do { assumed = old; if (!(__longlong_as_double((long long)assumed) < v)) break; old = atomicCAS(ad, assumed, (unsigned long long)__double_as_longlong(v)); } while (assumed != old); } }
+__global__ void __launch_bounds__(256, 4) k_stat(Geo g, StatArgs a) {
+  const long long nc_ = (long long)g.n[0] * g.n[1] * g.n[2];
+  const long long base = (long long)blockIdx.x * (256 * STAT_CPT) + threadIdx.x;
+  double acc[3][9];
+#pragma unroll
+  for (int ph = 0; ph < 3; ++ph) {
+#pragma unroll
+    for (int q = 0; q < 7; ++q) acc[ph][q] = 0.;
+    acc[ph][7] = 1e300; acc[ph][8] = -1e300;
+  }
+#pragma unroll 2
+  for (int r = 0; r < STAT_CPT; ++r) {
+    const long long c_ = base + 256LL * r;
+    if (c_ >= nc_) break;
+    int i, j, k;
+    if (nc_ < (1LL << 31)) {
+      const unsigned c32 = (unsigned)c_, nx = (unsigned)g.n[0], nxy = nx * (unsigned)g.n[1];
+      const unsigned k_ = c32 / nxy, r_ = c32 - k_ * nxy, j_ = r_ / nx;
+      k = (int)k_; j = (int)j_; i = (int)(r_ - j_ * nx);
+    } else { i = (int)(c_ % g.n[0]); j = (int)((c_ / g.n[0]) % g.n[1]); k = (int)(c_ / ((long long)g.n[0] * g.n[1])); }
+    double x[3]; cell_center(g, i, j, k, x);
+    double uv[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) uv[d] = d < DIM ? a.u[d][c_] : 0.;
+#pragma unroll
+    for (int ph = 0; ph < 3; ++ph) {
+      if (ph < a.np) {
+        const double w = a.vf[ph][c_] * g.vol;
+        acc[ph][0] += w;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) { acc[ph][1 + d] += x[d] * w; acc[ph][4 + d] += uv[d] * w; }
+        const double pd = a.pd[ph][c_];
+        acc[ph][7] = pd < acc[ph][7] ? pd : acc[ph][7];
+        acc[ph][8] = acc[ph][8] < pd ? pd : acc[ph][8];
       }
+    }
+  }
+  __shared__ double sm[27][8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int ph = 0; ph < 3; ++ph) {
+    if (ph < a.np) {
+#pragma unroll
+      for (int q = 0; q < 9; ++q) {
+        double v = acc[ph][q];
+        if (q < 7) v = warp_sum(v); else if (q == 7) v = warp_min(v); else v = warp_max(v);
+        if (lane == 0) sm[ph * 9 + q][w] = v;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 27 && threadIdx.x / 9 < a.np) {
+    const int ph = threadIdx.x / 9, q = threadIdx.x % 9;
+    double v = sm[threadIdx.x][0];
+    for (int t = 1; t < 8; ++t) { const double o = sm[threadIdx.x][t]; v = q < 7 ? v + o : (q == 7 ? (o < v ? o : v) : (v < o ? o : v)); }
+    if (q < 7) atomicAdd(&a.out[ph * 12 + q], v);
+    else {   // signed doubles: CAS loop
+      unsigned long long* ad = (unsigned long long*)&a.out[ph * 12 + q]; unsigned long long old = *ad, assumed;
+      do {
+        assumed = old;
+        const double cur = __longlong_as_double((long long)assumed);
+        if (q == 7 ? !(v < cur) : !(cur < v)) break;
+        old = atomicCAS(ad, assumed, (unsigned long long)__double_as_longlong(v));
+      } while (assumed != old);
     }
   }
 }

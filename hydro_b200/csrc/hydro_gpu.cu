@@ -19,6 +19,7 @@
 #include "hg_slab.cuh"
 #include "hg_gs_tiled.cuh"
 #include "hg_lu_tiled.cuh"
+#include "hg_fast.cuh"
 
 enum { L_TC = 0, L_TP = 1, L_IC = 2, L_IP = 3 };
 
@@ -64,6 +65,10 @@ struct hg_state {
   // lu as a dataflow of column boxes (hg_lu_tiled.cuh)
   bool lu_tiled = false; int2* lt_boxes = nullptr; int lt_nboxes = 0, lt_nbi = 0; int* lt_progress = nullptr; int* lt_ctl = nullptr;
   int num_sms = 0;
+  // interior kernels (hg_fast.cuh): byte mask of the cells that keep the generic kernels, their list, Geo of the list launches
+  // [0]: radius-1 stencils (SIMPLE iteration), [1]: radius 2 (advection)
+  bool fast = false; unsigned char* slow = nullptr; int* slow_list = nullptr; int nslow = 0;
+  unsigned char* slow2 = nullptr; int* slow2_list = nullptr; int nslow2 = 0;
   double* resid = nullptr;    // per-iteration convergence indicators of the current step (device, 4096)
   double* scal = nullptr;     // device scalars: [0] resid, [1] auto dt, [2..] stat (36), then diffs
   int* flag = nullptr;        // [0] scratch NaN flag (immediate checks), [1] any-excluded flag, [4..11] deferred NaN flags of a step
@@ -150,6 +155,8 @@ static void tpop(hg_state* s) {
   do { if ((s)->dim == 3) { KERN<3><<<grid, block, 0, (s)->st>>>(__VA_ARGS__); }             \
        else { KERN<2><<<grid, block, 0, (s)->st>>>(__VA_ARGS__); } ++(s)->launches; } while (0)
 
+static Geo list_geo(const hg_state* s, int R = 1) { Geo g = s->geo; g.cells = R == 1 ? s->slow_list : s->slow2_list; g.ncells = R == 1 ? s->nslow : s->nslow2; return g; }
+static dim3 fast_grid(const hg_state* s) { return dim3((s->n[0] + 31) / 32, (s->n[2] + FT_K - 1) / FT_K, s->n[1]); }
 static CP3 cp3(double* const a[3]) { CP3 r; for (int d = 0; d < 3; ++d) r.p[d] = a[d]; return r; }
 static P3 p3(double* const a[3]) { P3 r; for (int d = 0; d < 3; ++d) r.p[d] = a[d]; return r; }
 
@@ -556,6 +563,12 @@ static int gt_check(hg_state* s) {   // after the sweeps: did a dependency wait 
 }
 
 static int lt_check(hg_state* s);
+static void launch_pcorr(hg_state* s) {   // p' back to the natural layout, p_curr = p_prev + alpha p'
+  const double alpha = s->cfg.pressure_relaxation_factor;
+  if (s->dim == 3) k_ft_pcorr<<<fast_grid(s), FT_THREADS, 0, s->st>>>(s->geo, s->PP, s->p[L_IP], alpha, s->pc, s->p[L_IC]);
+  else k_pcorr<2><<<nblk(s->nc), 256, 0, s->st>>>(s->geo, s->PP, s->p[L_IP], alpha, s->pc, s->p[L_IC]);
+  ++s->launches;
+}
 static int solve_pressure(hg_state* s) {
   const hg_config& c = s->cfg;
   int it = 0; double df = 0.;
@@ -575,7 +588,7 @@ static int solve_pressure(hg_state* s) {
     double* defer_out = (s->defer && s->world == 1 && s->nsolves < 4096) ? s->sorres + 2 * s->nsolves : nullptr;
     if (int rc = run_sor(s, s->PP, s->nsh, c.lu_relaxed_tolerance, c.lu_relaxed_num_iters_limit, launch, &it, &df, defer_out)) return rc;
     if (!s->defer && s->gs_tiled) if (int rc = gt_check(s)) return rc;   // inside hg_step: part of the step's status block
-    DIMSEL(s, k_pcorr, nblk(s->nc), 256, s->geo, s->PP, s->p[L_IP], c.pressure_relaxation_factor, s->pc, s->p[L_IC]);
+    launch_pcorr(s);
   } else if (c.linear_solver_pressure == HG_LS_JACOBI) {
     // natural layout: constants back from the sheared array, rows regenerated from d_c
     DIMSEL(s, k_from_sheared, nblk(s->nc), 256, s->geo, s->RP, s->w1);
@@ -583,7 +596,7 @@ static int solve_pressure(hg_state* s) {
                             c.lu_relaxed_relaxation_factor, &it, &df)) return rc;
     // p_curr = p_prev + alpha p'
     DIMSEL(s, k_to_sheared, nblk(s->nc), 256, s->geo, s->pc, s->PP);
-    DIMSEL(s, k_pcorr, nblk(s->nc), 256, s->geo, s->PP, s->p[L_IP], c.pressure_relaxation_factor, s->pc, s->p[L_IC]);
+    launch_pcorr(s);
   } else if (c.linear_solver_pressure == HG_LS_LU_RELAXED) {
     P7 rows;
     if (s->dim == 3) {
@@ -596,7 +609,7 @@ static int solve_pressure(hg_state* s) {
     }
     if (int rc = run_lu_relaxed(s, s->RP, s->PP, s->X[0], s->X[1], c.lu_relaxed_tolerance, c.lu_relaxed_num_iters_limit,
                                 c.lu_relaxed_relaxation_factor, &it, &df)) return rc;
-    DIMSEL(s, k_pcorr, nblk(s->nc), 256, s->geo, s->PP, s->p[L_IP], c.pressure_relaxation_factor, s->pc, s->p[L_IC]);
+    launch_pcorr(s);
   } else {
     s->err = "linear_solver_pressure: lu is not iterated for the pressure system on the GPU path";
     return HG_ERR_INVALID;
@@ -728,7 +741,7 @@ static int calc_stat(hg_state* s, hg_step_stats* st, bool with_status) {
   for (int p = 0; p < 3; ++p) { a.vf[p] = s->vf[p]; a.pd[p] = s->pd[p][L_TC]; }
   for (int d = 0; d < 3; ++d) a.u[d] = s->u[L_TC][d] ? s->u[L_TC][d] : s->zero;
   a.out = s->scal + ST_STAT;
-  DIMSEL(s, k_stat, nblk(s->nc), 256, s->geo, a);
+  DIMSEL(s, k_stat, nblk(s->nc, 256 * STAT_CPT), 256, s->geo, a);
   int nvals = 36;
   if (with_status) {
     const double* rl = s->iter_count > 0 ? s->resid + (s->iter_count - 1 < 4095 ? s->iter_count - 1 : 4095) : nullptr;
@@ -835,6 +848,54 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
   // from here on: *_IP hold the state the iteration starts from
 
   XCH(s, 1, s->u[L_IP][0], s->u[L_IP][1], s->u[L_IP][2], s->p[L_IP]);
+  const bool fast = s->fast;
+  const Geo gl = list_geo(s);
+  const unsigned gbl = nblk(s->nslow);
+  const dim3 fg = fast_grid(s);
+  if (fast) {
+    // interior cells: gradients + restored force in one pass, then source + assembly + transpose in one pass (hg_fast.cuh);
+    // the listed cells (near walls / obstacle / fixed-pressure cell) keep the generic kernels
+    tpush(s, "fluid.0-1.gradients");
+    { FaArgs a;
+      for (int d = 0; d < 3; ++d) { a.u[d] = s->u[L_IP][d]; a.force[d] = s->force[d]; a.fcr[d] = s->fcr[d]; a.gp[d] = s->gp[d]; }
+      a.p = s->p[L_IP];
+      for (int q = 0; q < 9; ++q) a.G[q] = s->G[q];
+      k_fa_grad<<<fg, FT_THREADS, 0, s->st>>>(s->geo, s->slow, a); ++s->launches; }
+    P9 G; for (int q = 0; q < 9; ++q) G.p[q] = s->G[q];
+    if (s->nslow) {
+      k_pre<3><<<gbl, 256, 0, s->st>>>(gl, cp3(s->force), s->p[L_IP], p3(s->fcr), p3(s->gp)); ++s->launches;
+      k_velgrad<3><<<gbl, 256, 0, s->st>>>(gl, cp3(s->u[L_IP]), G); ++s->launches;
+    }
+    tpop(s);
+    if (s->world > 1) if (int rc = slab_exchange(s, s->G, 9, 1)) return rc;
+    tpush(s, "fluid.2.convection-diffusion");
+    const int use_stf = (c.num_phases >= 2 && c.sigma != 0.) ? 1 : 0;
+    if (s->nslow) {
+      P9c Gc; for (int q = 0; q < 9; ++q) Gc.p[q] = s->G[q];
+      k_source<3><<<gbl, 256, 0, s->st>>>(gl, Gc, s->mu, cp3(s->gp), cp3(s->fcr), cp3(s->stforce), use_stf, p3(s->fs)); ++s->launches;
+      AsmArgs a;
+      for (int n = 0; n < 3; ++n) { a.prev[n] = s->u[L_IP][n]; a.tc[n] = s->u[L_TC][n]; a.tp[n] = s->u[L_TP][n]; a.src[n] = s->fs[n]; a.R[n] = s->R[n]; }
+      for (int q = 0; q < 9; ++q) a.grad[q] = s->G[q];
+      a.rho = s->rho; a.mu = s->mu; a.F = s->F[L_IP];
+      bdf_coeffs(s->dt, c.time_second_order, a.co);
+      a.relax = c.velocity_relaxation_factor;
+      a.coeffsum = s->dc; a.coeffsum_div = 3.; a.out_sheared = 1;
+      for (int t = 0; t < 7; ++t) a.A[t] = s->A[t];
+      k_assemble<3, K_VEL, 3><<<gbl, 256, 0, s->st>>>(gl, a); ++s->launches;
+    }
+    { FbArgs a;
+      for (int n = 0; n < 3; ++n) { a.prev[n] = s->u[L_IP][n]; a.tc[n] = s->u[L_TC][n]; a.tp[n] = s->u[L_TP][n];
+                                    a.gp[n] = s->gp[n]; a.fcr[n] = s->fcr[n]; a.stf[n] = s->stforce[n]; a.out[7 + n] = s->R[n]; }
+      for (int q = 0; q < 9; ++q) a.G[q] = s->G[q];
+      for (int t = 0; t < 7; ++t) a.out[t] = s->A[t];
+      a.rho = s->rho; a.mu = s->mu; a.F = s->F[L_IP]; a.use_stf = use_stf;
+      bdf_coeffs(s->dt, c.time_second_order, a.co);
+      a.relax = c.velocity_relaxation_factor; a.coeffsum = s->dc;
+      k_fb_momentum<<<fg, FT_THREADS, 0, s->st>>>(s->geo, s->slow, a); ++s->launches; }
+    if (int rc = solve_lu(s, 3)) return rc;
+    k_ft_apply_corr<3><<<fg, FT_THREADS, 0, s->st>>>(s->geo, cp3(s->u[L_IP]), cp3(s->X), p3(s->u[L_IC])); ++s->launches;
+    tpop(s);
+  } else {
   tpush(s, "fluid.0.pressure-gradient");
   DIMSEL(s, k_pre, gb, 256, s->geo, cp3(s->force), s->p[L_IP], p3(s->fcr), p3(s->gp));
   tpop(s);
@@ -873,7 +934,26 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
     else { k_apply_corr<2, 2><<<gb, 256, 0, s->st>>>(s->geo, cp3(s->u[L_IP]), cp3(s->X), p3(s->u[L_IC])); }
     ++s->launches; }
   tpop(s);
+  }
   XCH(s, 1, s->u[L_IC][0], s->u[L_IC][1], s->u[L_IC][2], s->gp[0], s->gp[1], s->gp[2], s->fcr[0], s->fcr[1], s->fcr[2], s->dc);
+  if (fast && s->gs_tiled) {
+    // Rhie-Chow fluxes + rows of the pressure-correction system, packed for k_gs_tiled, in one pass over the interior cells
+    tpush(s, "fluid.3-5.fluxes+pressure-system");
+    { FcArgs a;
+      for (int d = 0; d < 3; ++d) { a.us[d] = s->u[L_IC][d]; a.gp[d] = s->gp[d]; a.fcr[d] = s->fcr[d]; a.force[d] = s->force[d]; a.meshvel[d] = c.meshvel[d]; }
+      a.pprev = s->p[L_IP]; a.dc = s->dc; a.rc = c.rhie_chow_factor; a.Fs = s->Fs; a.co5 = s->co5;
+      for (int q = 0; q < 5; ++q) a.co[q] = s->CO + q * s->co5.arr;
+      k_fc_flux_rows<<<fg, FT_THREADS, 0, s->st>>>(s->geo, s->slow, a); ++s->launches; }
+    if (s->nslow) {
+      FstarArgs a;
+      for (int d = 0; d < 3; ++d) { a.us[d] = s->u[L_IC][d]; a.gp[d] = s->gp[d]; a.fcr[d] = s->fcr[d]; a.force[d] = s->force[d]; a.meshvel[d] = c.meshvel[d]; }
+      a.pprev = s->p[L_IP]; a.dc = s->dc; a.rc = c.rhie_chow_factor; a.Fs = s->Fs;
+      k_fstar<3><<<gbl, 256, 0, s->st>>>(gl, a); ++s->launches;
+      k_prhs_co5<<<gbl, 256, 0, s->st>>>(gl, s->Fs, s->dc, s->CO, s->co5); ++s->launches;
+    }
+    if (s->geo.zlo > 0) { k_gt_cz_halo<<<nblk(s->nxy), 256, 0, s->st>>>(s->geo, s->dc, s->CO, s->co5); ++s->launches; }
+    tpop(s);
+  } else {
   tpush(s, "fluid.3.momentum-interpolation");
   { FstarArgs a;
     for (int d = 0; d < 3; ++d) { a.us[d] = s->u[L_IC][d]; a.gp[d] = s->gp[d]; a.fcr[d] = s->fcr[d]; a.force[d] = s->force[d]; a.meshvel[d] = c.meshvel[d]; }
@@ -899,6 +979,7 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
     DIMSEL(s, k_prhs, gb, 256, s->geo, s->Fs, s->dc, 1, s->RP, s->D, s->CYs, s->CZs, nullptr);
   }
   tpop(s);
+  }
   tpush(s, "fluid.6.pressure-solve");
   if (int rc = solve_pressure(s)) return rc;
   tpop(s);
@@ -906,7 +987,10 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
   tpush(s, "fluid.7.correction");
   { CorrArgs a; a.pc = s->pc; a.dc = s->dc; a.Fs = s->Fs; a.F = s->F[L_IC];
     for (int d = 0; d < 3; ++d) a.u[d] = s->u[L_IC][d];
-    DIMSEL(s, k_correct, gb, 256, s->geo, a); }
+    if (fast) {
+      k_fd_correct<<<fg, FT_THREADS, 0, s->st>>>(s->geo, s->slow, a); ++s->launches;
+      if (s->nslow) { k_correct<3><<<gbl, 256, 0, s->st>>>(gl, a); ++s->launches; }
+    } else DIMSEL(s, k_correct, gb, 256, s->geo, a); }
   tpop(s);
   // convergence indicator (fluid.hpp:174-179): computed now into resid[iteration], fetched lazily
   double* rdst = s->resid + (s->iter_count < 4096 ? s->iter_count : 4095);
@@ -987,7 +1071,10 @@ extern "C" int hg_advection_step(hg_handle s) {   // advection.hpp:417-545
     for (int stage = 0; stage < num_stages; ++stage) {
       out = bufs[stage % 2];
       XCH(s, 2, const_cast<double*>(in));
-      DIMSEL(s, k_advect, nblk(s->nc), 256, s->geo, in, s->pd_init[ph], s->F[L_TC], s->dt_adv, num_stages, stage, out);
+      if (s->fast) {
+        k_fe_advect<<<fast_grid(s), FT_THREADS, 0, s->st>>>(s->geo, s->slow2, in, s->F[L_TC], s->dt_adv, num_stages, stage, out); ++s->launches;
+        if (s->nslow2) { k_advect<3><<<nblk(s->nslow2), 256, 0, s->st>>>(list_geo(s, 2), in, s->pd_init[ph], s->F[L_TC], s->dt_adv, num_stages, stage, out); ++s->launches; }
+      } else DIMSEL(s, k_advect, nblk(s->nc), 256, s->geo, in, s->pd_init[ph], s->F[L_TC], s->dt_adv, num_stages, stage, out);
       in = out;
     }
     // FinishStep: time_curr = iter_curr
@@ -1431,6 +1518,27 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     }
     const int kg = (int)(best / g.sz);
     if (kg >= s->k0 - g.zlo && kg < s->k1 + g.zhi) g.pfix = best - (long long)s->k0 * g.sz;   // local index, may be in a halo plane
+  }
+  // interior / listed cells (hg_fast.cuh): 3-D meshes below 2^31 cells; HYDRO_FAST=0 keeps the generic kernels everywhere
+  { const char* e = getenv("HYDRO_FAST");
+    s->fast = dim == 3 && s->nc < (1LL << 31) && !(e && !strcmp(e, "0")); }
+  if (s->fast) {
+    for (int R = 1; R <= 2; ++R) {
+      unsigned char*& mask = R == 1 ? s->slow : s->slow2;
+      int*& lst = R == 1 ? s->slow_list : s->slow2_list;
+      int& cnt = R == 1 ? s->nslow : s->nslow2;
+      if (dalloc(s, &mask, s->nc, false)) return fail_create(s, HG_ERR_CUDA, "allocation failed: " + s->err);
+      k_fast_mask<<<nblk(s->nc), 256, 0, s->st>>>(g, R, mask);
+      std::vector<unsigned char> hm((size_t)s->nc);
+      if (cudaMemcpyAsync(hm.data(), mask, (size_t)s->nc, cudaMemcpyDeviceToHost, s->st) != cudaSuccess ||
+          cudaStreamSynchronize(s->st) != cudaSuccess) return fail_create(s, HG_ERR_CUDA, "k_fast_mask failed");
+      std::vector<int> list;
+      for (long long c = 0; c < s->nc; ++c) if (hm[(size_t)c]) list.push_back((int)c);
+      cnt = (int)list.size();
+      if (dalloc(s, &lst, std::max(cnt, 1), false)) return fail_create(s, HG_ERR_CUDA, "allocation failed: " + s->err);
+      if (cnt) cudaMemcpy(lst, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    if (s->nslow == s->nc) s->fast = false;   // no interior cell
   }
   s->dt = cfg->dt; s->dt_adv = cfg->dt * cfg->advection_dt_factor;
   if (s->world > 1) {

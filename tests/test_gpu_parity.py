@@ -242,6 +242,34 @@ def test_lu_tiled_equals_hyperplane_kernel(case, monkeypatch):
         assert np.array_equal(fa[n], fb[n]), n
 
 
+@pytest.mark.parametrize("case", ["rt3d_40x36x20", "dam3d_64x20x24", "rt3d_9x5x4", "rt3d_70x19x33_split_stf", "rt3d_33x40x41_pfix"])
+def test_interior_kernels_equal_generic_kernels(case, monkeypatch):
+    """hg_fast.cuh: the cells whose radius-2 stencil is all inner faces take fused interior kernels (gradients; source +
+    assembly + transpose; fluxes + pressure rows + packing; correction; advection), the shell near walls / the obstacle /
+    the fixed-pressure cell keeps the generic kernels over a cell list.  Same arithmetic, operation by operation: every
+    field must equal the all-generic run (HYDRO_FAST=0) bit for bit."""
+    from hydro_b200.capi import Hydro
+    p = {"rt3d_40x36x20": cases.rt3d(8, Nx=40, Ny=36, Nz=20, lu_relaxed_num_iters_limit=9),
+         "dam3d_64x20x24": cases.broken_dam_3d(64, 20, 24, lu_relaxed_num_iters_limit=12),
+         "rt3d_9x5x4": cases.rt3d(8, Nx=9, Ny=5, Nz=4, lu_relaxed_num_iters_limit=11),
+         "rt3d_70x19x33_split_stf": cases.rt3d(8, Nx=70, Ny=19, Nz=33, lu_relaxed_num_iters_limit=7, tvd_split=1, sigma=0.05,
+                                               meshvel=(0.01, 0.02, -0.01), guess_extrapolation=0.5),
+         "rt3d_33x40x41_pfix": cases.rt3d(8, Nx=33, Ny=40, Nz=41, lu_relaxed_num_iters_limit=8, pressure_fixed_enable=1,
+                                          pressure_fixed_point=(0.5, 0.5, 0.5), pressure_fixed_value=0.25)}[case]
+    names = ["VELOCITY_X", "VELOCITY_Y", "VELOCITY_Z", "PRESSURE", "VOLUME_FLUX", "PARTIAL_DENSITY_0", "PARTIAL_DENSITY_1"]
+    res = []
+    for fast in ("1", "0"):
+        monkeypatch.setenv("HYDRO_FAST", fast)
+        h = Hydro(p)
+        st = [h.step() for _ in range(3)][-1]
+        res.append((st, {n: h.get(n) for n in names}))
+        h.close()
+    (sa, fa), (sb, fb) = res
+    assert sa.convergence_indicator == sb.convergence_indicator and sa.pressure_last_diff == sb.pressure_last_diff
+    for n in names:
+        assert np.array_equal(fa[n], fb[n]), n
+
+
 def test_gpu_tvd_split_and_surface_tension():
     run_both(cases.broken_dam_2d(40, 24, tvd_split=1, sigma=0.07, lu_relaxed_num_iters_limit=40), 2, tol=1e-11)
 
