@@ -234,7 +234,12 @@ def run_b200(args, rank, local_rank, world):
     strong = args.scaling == "strong"
     parity = None
     if world > 1:
-        parity = slab_parity_check(dist, rank, world, local_rank)
+        parity = slab_parity_check(dist, rank, world, local_rank, n=args.parity_size)
+        if args.parity_only:
+            if rank == 0:
+                print(json.dumps({"parity_check": parity, "n_gpus": world}))
+            dist.destroy_process_group()
+            return
         if strong:
             # strong scaling: the n^3 mesh of the single-GPU run, cut into z-slabs
             mesh = (n, n, n)
@@ -427,6 +432,8 @@ def main():
     ap.add_argument("--no-as-configured", action="store_true")
     ap.add_argument("--workload", default="rt", choices=["rt", "dam"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--parity-only", action="store_true", help="N > 1: only the slab-vs-single-GPU bit-exactness check over CUDA IPC")
+    ap.add_argument("--parity-size", type=int, default=64)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -36,6 +36,16 @@ constexpr int FT_PITCH = 32;   // tile row pitch (doubles): a diagonal read (il 
   const bool in = i < (g).n[0] && k < (g).n[2];                                             \
   const long long c = cidx(g, i, j, k);
 
+#ifndef FT_PREFETCH
+#define FT_PREFETCH 1
+#endif
+// The interior kernels are gathers with ~100 loads per cell and few warps per SM: their first touch of every input row is
+// requested up front (no register is tied up, all rows of a CTA are in flight at once), the loads then hit L2.
+DV void ft_prefetch(const void* p) {
+#if FT_PREFETCH
+  asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#endif
+}
 DV double ft_avg(double a, double b) { return a * (1. - 0.5) + b * 0.5; }   // Interpolate on an inner face (solver.hpp:425-426)
 // Gradient(Interpolate(u))[d] of a cell with inner faces (solver.hpp:658-677): um, uc, up = u at c - e_d, c, c + e_d
 DV double ft_grad(double um, double uc, double up, double aneg, double apos, const HgDiv& dvol) {
@@ -72,7 +82,11 @@ struct FaArgs {
 };
 __global__ void __launch_bounds__(FT_THREADS, 6) k_fa_grad(Geo g, const unsigned char* __restrict__ slow, FaArgs a) {
   FT_PROLOG(g)
-  if (!in || slow[c]) return;
+  if (!in) return;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { ft_prefetch(a.u[d] + c); ft_prefetch(a.force[d] + c); }
+  ft_prefetch(a.p + c);
+  if (slow[c]) return;
   const HgDiv dvol = hg_div_prepare(g.vol);
   const long long off[3] = {1, g.sy, g.sz};
 #pragma unroll
@@ -127,6 +141,9 @@ DV void ft_store_diagonals(const double* tile, const unsigned* act, double* cons
 }
 
 // ------------------------------------------------------------------------------------------------ K_source + K_assemble
+#ifndef FB_MINB
+#define FB_MINB 4
+#endif
 struct FbArgs {
   const double* prev[3]; const double* tc[3]; const double* tp[3];
   const double* G[9]; const double* rho; const double* mu; const double* F;
@@ -135,10 +152,18 @@ struct FbArgs {
   double* out[10];     // A[7] (z-,y-,x-,d,x+,y+,z+) and R[3], hyperplane-major
   double* coeffsum;    // natural
 };
-__global__ void __launch_bounds__(FT_THREADS, 3) k_fb_momentum(Geo g, const unsigned char* __restrict__ slow, FbArgs a) {
+__global__ void __launch_bounds__(FT_THREADS, FB_MINB) k_fb_momentum(Geo g, const unsigned char* __restrict__ slow, FbArgs a) {
   __shared__ double tile[10 * FT_K * FT_PITCH];
   __shared__ unsigned act[FT_K];
   FT_PROLOG(g)
+  if (in) {
+#pragma unroll
+    for (int q = 0; q < 9; ++q) ft_prefetch(a.G[q] + c);
+#pragma unroll
+    for (int n = 0; n < 3; ++n) { ft_prefetch(a.prev[n] + c); ft_prefetch(a.tc[n] + c); ft_prefetch(a.tp[n] + c); ft_prefetch(a.gp[n] + c); ft_prefetch(a.fcr[n] + c);
+                                  if (a.use_stf) ft_prefetch(a.stf[n] + c); ft_prefetch(a.F + fidx(g, n, i, j, k)); }
+    ft_prefetch(a.rho + c); ft_prefetch(a.mu + c);
+  }
   const bool fast = in && !slow[c];
   const unsigned bal = __ballot_sync(0xffffffffu, fast);
   if (tx == 0) act[ty] = bal;
@@ -274,6 +299,11 @@ __global__ void __launch_bounds__(FT_THREADS, 4) k_fc_flux_rows(Geo g, const uns
   __shared__ double tile[5 * FT_K * FT_PITCH];
   __shared__ unsigned act[FT_K];
   FT_PROLOG(g)
+  if (in) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { ft_prefetch(a.us[d] + c); ft_prefetch(a.gp[d] + c); ft_prefetch(a.fcr[d] + c); ft_prefetch(a.force[d] + c); }
+    ft_prefetch(a.pprev + c); ft_prefetch(a.dc + c);
+  }
   const bool fast = in && !slow[c];
   const unsigned bal = __ballot_sync(0xffffffffu, fast);
   if (tx == 0) act[ty] = bal;
@@ -323,7 +353,11 @@ __global__ void __launch_bounds__(256, 4) k_prhs_co5(Geo g, const double* __rest
 // ------------------------------------------------------------------------------------------------ K_correct
 __global__ void __launch_bounds__(FT_THREADS, 4) k_fd_correct(Geo g, const unsigned char* __restrict__ slow, CorrArgs a) {
   FT_PROLOG(g)
-  if (!in || slow[c]) return;
+  if (!in) return;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { ft_prefetch(a.u[d] + c); ft_prefetch(a.Fs + fidx(g, d, i, j, k)); }
+  ft_prefetch(a.pc + c); ft_prefetch(a.dc + c);
+  if (slow[c]) return;
   const HgDiv dvol = hg_div_prepare(g.vol);
   const long long off[3] = {1, g.sy, g.sz};
   const double pcc = a.pc[c], dcc = a.dc[c];

@@ -476,7 +476,10 @@ static int gt_build_tasks(hg_state* s, int S, GtTask* tasks, int* ntasks) {
   // time, so that the shared rows are still in L2 when the second box asks for them.
   static const int WJ = getenv("HYDRO_GT_WJ") ? std::max(0, atoi(getenv("HYDRO_GT_WJ"))) : GT_TY;
   static const int WI = getenv("HYDRO_GT_WI") ? std::max(1, atoi(getenv("HYDRO_GT_WI"))) : GT_TX;
-  const int WG = WI + WJ + 2 * GT_B + 2;
+  // WG: the natural weight WI + WJ + 2B + 2 interleaves about ten groups (spatial neighbours of one group are then ~100 steps
+  // apart in time and their shared rows have left L2); a large WG claims group by group
+  static const int WG0 = getenv("HYDRO_GT_WG") ? atoi(getenv("HYDRO_GT_WG")) : 0;
+  const int WG = std::max(WG0, WI + WJ + 2 * GT_B + 2);
   for (int gI = 0; gI < NG; ++gI) for (int I = 0; I < NI; ++I) for (int J = 0; J < NJ; ++J)
     if (exists(I, J, gI)) keys.push_back({WI * I + WJ * J + WG * gI, gI, J, I});
   std::stable_sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.w < b.w; });

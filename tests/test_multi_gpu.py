@@ -65,3 +65,26 @@ def test_single_gpu_matches_tiled_default():
     stn, fn = parallel.run_local_ranks(p, 2, 1, FIELDS, devices=devs, solver_ctas=ctas)
     for n in FIELDS:
         assert np.array_equal(fn[n], f1[n]), n
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_one_process_per_gpu_over_ipc_equals_single_gpu(world):
+    """The path the scaling bench measures: one process per GPU (torchrun), CUDA IPC handles exchanged through
+    torch.distributed, halo planes / interface values / reductions as NVLink peer stores.  bench.py --parity-only gathers
+    the slab fields after two steps and compares them bit for bit with the single-GPU run of the same case (all ranks
+    claim the box-dataflow kernels).  Needs `world` visible devices."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs (the driver's GPU test box has one; gpurun --gpus %d runs it)" % (world, world))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29500 + world + os.getpid() % 200
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(root, "bench.py"),
+                        "--gpus", str(world), "--parity-only", "--parity-size", "48"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-1500:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    assert json.loads(line)["parity_check"].startswith("bit-exact"), line
