@@ -43,9 +43,11 @@ def workload_params(n, workload="rt", as_configured=False):
     return cases.rt3d(n, fixed_work=True)
 
 
-def weak_mesh(n, world):
-    """Mesh of the weak-scaling run: n^3 cells per GPU; y, x, z are doubled in turn (2: n x 2n x n, 4: 2n x 2n x n,
-    8: 2n x 2n x 2n); other rank counts extend z."""
+def weak_mesh(n, world, shape="cubic"):
+    """Mesh of the weak-scaling run, n^3 cells per GPU.  cubic: y, x, z are doubled in turn (2: n x 2n x n, 4: 2n x 2n x n,
+    8: 2n x 2n x 2n; other rank counts extend z).  column: n x n x (n world) -- every z-slab is the single-GPU n^3 block."""
+    if shape == "column":
+        return (n, n, n * world)
     m = [n, n, n]
     w, order, q = world, (1, 0, 2), 0
     while w > 1 and w % 2 == 0:
@@ -246,7 +248,7 @@ def run_b200(args, rank, local_rank, world):
         else:
             # weak scaling: n^3 cells per GPU, same cell size; z-slabs of a mesh that is kept as cubic as possible
             # (the lexicographic sweeps are a wavefront over i+j+k: its length, nx+ny+nz, is the serial part)
-            mesh = weak_mesh(n, world)
+            mesh = weak_mesh(n, world, args.weak_mesh)
             fx, fy, fz = mesh[0] / n, mesh[1] / n, mesh[2] / n
             B, B1 = p["B"], p["B1"]
             p.update(Nx=mesh[0], Ny=mesh[1], Nz=mesh[2], B=(B[0] * fx, B[1] * fy, B[2] * fz), B1=(B1[0] * fx, B1[1] * fy, B1[2] * fz))
@@ -432,6 +434,7 @@ def main():
     ap.add_argument("--no-as-configured", action="store_true")
     ap.add_argument("--workload", default="rt", choices=["rt", "dam"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--weak-mesh", default="cubic", choices=["cubic", "column"])
     ap.add_argument("--parity-only", action="store_true", help="N > 1: only the slab-vs-single-GPU bit-exactness check over CUDA IPC")
     ap.add_argument("--parity-size", type=int, default=64)
     args = ap.parse_args()

@@ -136,7 +136,12 @@ __global__ void k_mail_wait(double* mymail, int world, unsigned long long v) {
   if (t < world) slab_wait(slab_flags(mymail, world) + SF_MAIL0 + t, v, slab_flags(mymail, world) + SF_ERR);
 }
 
-constexpr int SLAB_LL_PLANES = 10;
+// planes 0..9 as listed at Slab::ll; then the box-dataflow sweeps (k_gs_tiled<LINK>): SLAB_GB "up" planes (top-plane values of
+// the lower neighbour, one per sweep of a group), 2 x SLAB_GB "down" planes (the upper neighbour's bottom planes after the last
+// sweep of a group, double-buffered by group parity) and 2 x SLAB_GB planes for the checkpoint of the "down" planes
+constexpr int SLAB_GB = 8;           // largest sweep group
+constexpr int SLAB_LL_UP = 10, SLAB_LL_DOWN = SLAB_LL_UP + SLAB_GB, SLAB_LL_DOWN_SAVE = SLAB_LL_DOWN + 2 * SLAB_GB;
+constexpr int SLAB_LL_PLANES = SLAB_LL_DOWN_SAVE + 2 * SLAB_GB;
 // tagged 16-byte transport of one double (the scheme of NCCL's LL protocol): each 8-byte half is stored atomically
 // and carries the tag, so a reader that sees the expected tag in both halves has the whole value
 DV void ll_store(uint4* p, double v, unsigned tag) {
@@ -170,6 +175,16 @@ struct SlabLink {
   uint4* to_lo;                   // the lower neighbour's "from above" plane
   uint4* to_hi;                   // the upper neighbour's "from below" plane
   unsigned tag0;                  // tag of "before the first sweep of the solve"; sweep s of the solve carries tag0 + s + 1
+  // box-dataflow sweeps (k_gs_tiled<LINK>): no value travels downwards inside a sweep group.  A slab also runs the first
+  // nsw-1-ds planes of the slab above as ghost planes in sweep ds of a group (the same arithmetic on the same inputs as the
+  // owner: identical bits), so its top cell finds its z+ value in its own frames; the owner sends the final values of its
+  // bottom planes once per group (down), the lower slab its top-plane value of every sweep (up, one plane per sweep of the
+  // group: the owner has consumed a group's values before it produces what the next group's top cells wait for).
+  const uint4* up_from;           // mine [sweep of the group][nxy], written by the lower neighbour
+  uint4* up_to;                   // the upper neighbour's up_from
+  const uint4* down_from;         // mine [group parity][plane][nxy], written by the upper neighbour
+  uint4* down_to;                 // the lower neighbour's down_from
+  int gbase;                      // groups of this solve launched before this launch (group parity)
   unsigned long long* err;        // local error word (wait timed out)
 };
 

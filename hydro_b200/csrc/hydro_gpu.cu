@@ -61,6 +61,7 @@ struct hg_state {
   GtPlan gt_plans[GT_PLAN_SLOTS];
   int gt_plan_cap = 0; long long gt_plan_clock = 0;
   int* gt_ctl = nullptr;
+  int gt_gbase = 0;                           // sweep groups of the current solve launched so far (parity of the slabs' "down" planes)
   unsigned long long* gt_clk = nullptr;
   // lu as a dataflow of column boxes (hg_lu_tiled.cuh)
   bool lu_tiled = false; int2* lt_boxes = nullptr; int lt_nboxes = 0, lt_nbi = 0; int* lt_progress = nullptr; int* lt_ctl = nullptr;
@@ -187,6 +188,24 @@ static int slab_exchange(hg_state* s, std::initializer_list<double*> arrs, int p
   for (double* q : arrs) if (q) v.push_back(q);
   return slab_exchange(s, v.data(), (int)v.size(), planes);
 }
+// k_gs_tiled on slabs: rows of the first GT_B - 1 planes of every slab -> ghost hyperplanes of the slab below (same handshake
+// as slab_exchange: pack, flags, pull)
+static int gt_ghost_rows(hg_state* s) {
+  if (s->world <= 1 || !s->gs_tiled || GT_GHOST == 0) return 0;
+  if (!s->slab.linked) { s->err = "multi-GPU handle used before hg_ipc_import"; return HG_ERR_INVALID; }
+  Slab& sl = s->slab;
+  const unsigned long long v = ++sl.xseq;
+  const int parity = (int)(v & 1ull);
+  const unsigned blocks = nblk(5LL * GT_GHOST * s->nxy);
+  if (sl.has_lo) { k_gt_ghost_pack<<<blocks, 256, 0, s->st>>>(s->geo, s->CO, s->co5, sl.xbuf, parity); ++s->launches; }
+  unsigned long long* f_lo = sl.has_lo ? slab_flags(sl.mail_peer[s->rank - 1], s->world) + SF_X_HI : nullptr;
+  unsigned long long* f_hi = sl.has_hi ? slab_flags(sl.mail_peer[s->rank + 1], s->world) + SF_X_LO : nullptr;
+  k_slab_signal<<<1, 1, 0, s->st>>>(f_lo, f_hi, v);
+  k_slab_wait<<<1, 1, 0, s->st>>>(sl.has_lo, sl.has_hi, slab_flags(sl.mail, s->world), v);
+  if (sl.has_hi) { k_gt_ghost_unpack<<<blocks, 256, 0, s->st>>>(s->geo, s->CO, s->co5, sl.xbuf_hi, parity); ++s->launches; }
+  s->launches += 2;
+  return 0;
+}
 // all-gather of n device doubles from every rank into host memory out[world][n] (stream-synchronising)
 static int slab_gather(hg_state* s, const double* dev_vals, int n, std::vector<double>& out) {
   out.assign((size_t)s->world * n, 0.);
@@ -249,6 +268,10 @@ static SlabLink slab_link(hg_state* s, int which) {
   L.from_hi = sl.ll + (which ? 5 : 1) * nxy;
   L.to_lo = sl.has_lo ? sl.ll_lower + (which ? 5 : 1) * nxy : nullptr;
   L.to_hi = sl.has_hi ? sl.ll_upper + (which ? 2 : 0) * nxy : nullptr;
+  L.up_from = sl.ll + SLAB_LL_UP * nxy; L.down_from = sl.ll + SLAB_LL_DOWN * nxy;
+  L.up_to = sl.has_hi ? sl.ll_upper + SLAB_LL_UP * nxy : nullptr;
+  L.down_to = sl.has_lo ? sl.ll_lower + SLAB_LL_DOWN * nxy : nullptr;
+  L.gbase = s->gt_gbase;
   L.tag0 = which ? sl.lu_seq * 4u : sl.solve_seq * 2048u;
   L.err = slab_flags(sl.mail, s->world) + SF_ERR;
   return L;
@@ -316,7 +339,10 @@ static int run_sor(hg_state* s, double* x, long long nx_, double tol, int limit,
     if (s->world <= 1) return 0;
     ++s->slab.solve_seq;
     k_ll_fill<<<nblk(2 * s->nxy), 256, 0, s->st>>>(s->slab.ll, 2 * s->nxy, s->slab.solve_seq * 2048u);
-    ++s->launches;
+    // box-dataflow sweeps: the ghost planes of the first group start from the initial guess 0
+    k_ll_fill<<<nblk(2LL * SLAB_GB * s->nxy), 256, 0, s->st>>>(s->slab.ll + SLAB_LL_DOWN * s->nxy, 2LL * SLAB_GB * s->nxy, s->slab.solve_seq * 2048u);
+    s->gt_gbase = 0;
+    s->launches += 2;
     return slab_sync(s);
   };
   if (int rc = ll_reset()) return rc;
@@ -356,7 +382,11 @@ static int run_sor(hg_state* s, double* x, long long nx_, double tol, int limit,
   while (done < max_total) {
     int n = std::min(chunk, max_total - done);
     CK(cudaMemcpyAsync(s->PPsave, x, nx_ * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
-    if (s->world > 1) CK(cudaMemcpyAsync(s->slab.ll + 8 * s->nxy, s->slab.ll, 2 * s->nxy * sizeof(uint4), cudaMemcpyDeviceToDevice, s->st));
+    const int gbase_save = s->gt_gbase;
+    if (s->world > 1) {
+      CK(cudaMemcpyAsync(s->slab.ll + 8 * s->nxy, s->slab.ll, 2 * s->nxy * sizeof(uint4), cudaMemcpyDeviceToDevice, s->st));
+      CK(cudaMemcpyAsync(s->slab.ll + SLAB_LL_DOWN_SAVE * s->nxy, s->slab.ll + SLAB_LL_DOWN * s->nxy, 2LL * SLAB_GB * s->nxy * sizeof(uint4), cudaMemcpyDeviceToDevice, s->st));
+    }
     if (int rc = launch(done, done + n)) return rc;
     if (int rc = slab_reduce(s, s->diffs + done, n, 0, s->hdiffs + done)) return rc;
     int stop = -1;
@@ -364,7 +394,11 @@ static int run_sor(hg_state* s, double* x, long long nx_, double tol, int limit,
     if (stop >= 0) {
       if (stop != done + n - 1) {
         CK(cudaMemcpyAsync(x, s->PPsave, nx_ * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
-        if (s->world > 1) CK(cudaMemcpyAsync(s->slab.ll, s->slab.ll + 8 * s->nxy, 2 * s->nxy * sizeof(uint4), cudaMemcpyDeviceToDevice, s->st));
+        if (s->world > 1) {
+          CK(cudaMemcpyAsync(s->slab.ll, s->slab.ll + 8 * s->nxy, 2 * s->nxy * sizeof(uint4), cudaMemcpyDeviceToDevice, s->st));
+          CK(cudaMemcpyAsync(s->slab.ll + SLAB_LL_DOWN * s->nxy, s->slab.ll + SLAB_LL_DOWN_SAVE * s->nxy, 2LL * SLAB_GB * s->nxy * sizeof(uint4), cudaMemcpyDeviceToDevice, s->st));
+          s->gt_gbase = gbase_save;
+        }
         CK(cudaMemsetAsync(s->diffs + done, 0, n * sizeof(double), s->st));
         if (int rc = slab_sync(s)) return rc;
         if (int rc = launch(done, stop + 1)) return rc;
@@ -555,6 +589,7 @@ static int gt_launch(hg_state* s, int sb, int se, double omega) {
   CK(cudaGetLastError());
   if (e0) { cudaEventRecord(e1, s->st); s->prof_ev[0].push_back({e0, e1}); }
   ++s->launches;
+  s->gt_gbase += (se - sb + GT_B - 1) / GT_B;
   return 0;
 }
 static int gt_check(hg_state* s) {   // after the sweeps: did a dependency wait time out?
@@ -955,6 +990,7 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
       k_prhs_co5<<<gbl, 256, 0, s->st>>>(gl, s->Fs, s->dc, s->CO, s->co5); ++s->launches;
     }
     if (s->geo.zlo > 0) { k_gt_cz_halo<<<nblk(s->nxy), 256, 0, s->st>>>(s->geo, s->dc, s->CO, s->co5); ++s->launches; }
+    if (int rc = gt_ghost_rows(s)) return rc;
     tpop(s);
   } else {
   tpush(s, "fluid.3.momentum-interpolation");
@@ -973,6 +1009,7 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
       k_gt_shear_pack<<<dim3((s->n[0] + 31) / 32, s->n[1], (s->n[2] + 31) / 32), 256, 0, s->st>>>(s->geo, pa);
       ++s->launches;
       if (s->geo.zlo > 0) { k_gt_cz_halo<<<nblk(s->nxy), 256, 0, s->st>>>(s->geo, s->dc, s->CO, s->co5); ++s->launches; }
+      if (int rc = gt_ghost_rows(s)) return rc;
     } else {
       double* outs[4] = {s->RP, s->D, s->CYs, s->CZs};
       shear_arrays(s, s->An, outs, 4);
@@ -1377,7 +1414,8 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     // HYDRO_GS_KERNEL=hyperplane / HYDRO_GS_SLAB_KERNEL=hyperplane keep the pipelined hyperplane kernel (also used in 2-D)
     { const char* e = getenv("HYDRO_GS_KERNEL");
       const char* es = getenv("HYDRO_GS_SLAB_KERNEL");
-      const bool slab_ok = s->world == 1 || !(es && !strcmp(es, "hyperplane"));
+      // (a slab runs up to GT_B - 1 planes of the slab above as ghost planes and sends its bottom GT_B planes down)
+      const bool slab_ok = s->world == 1 || (!(es && !strcmp(es, "hyperplane")) && s->nzg / s->world >= GT_B);
       T.gs_tiled = dim == 3 && slab_ok && cfg->linear_solver_pressure == HG_LS_GAUSS_SEIDEL && !(e && !strcmp(e, "hyperplane")) &&
                    8LL * (GT_PAD + 2) * s->nxy < (1LL << 31);   // 32-bit byte offsets inside k_gs_tiled
     }
@@ -1558,6 +1596,10 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     cudaFuncGetAttributes(&fa, k_slab_pack); cudaFuncGetAttributes(&fa, k_slab_signal); cudaFuncGetAttributes(&fa, k_slab_wait);
     cudaFuncGetAttributes(&fa, k_slab_unpack); cudaFuncGetAttributes(&fa, k_mail_post); cudaFuncGetAttributes(&fa, k_mail_wait);
     cudaFuncGetAttributes(&fa, k_cz_halo<3>); cudaFuncGetAttributes(&fa, k_flag_to_double);
+    cudaFuncGetAttributes(&fa, k_gt_ghost_pack); cudaFuncGetAttributes(&fa, k_gt_ghost_unpack); cudaFuncGetAttributes(&fa, k_gt_cz_halo);
+    cudaFuncGetAttributes(&fa, k_fa_grad); cudaFuncGetAttributes(&fa, k_fb_momentum); cudaFuncGetAttributes(&fa, k_fc_flux_rows);
+    cudaFuncGetAttributes(&fa, k_fd_correct); cudaFuncGetAttributes(&fa, k_fe_advect); cudaFuncGetAttributes(&fa, k_prhs_co5);
+    cudaFuncGetAttributes(&fa, k_ft_apply_corr<3>); cudaFuncGetAttributes(&fa, k_ft_pcorr); cudaFuncGetAttributes(&fa, k_ll_fill);
     cudaGetLastError();
   }
   // no allocation after this point on the stepping path: cudaMalloc synchronises the device, which dead-locks
