@@ -298,10 +298,14 @@ def run_b200(args, rank, local_rank, world):
     gs_n, gs_ms = h.profile_read(0)
     lu_n, lu_ms = h.profile_read(1)
     h.profile_enable(False)
-    if os.environ.get("HYDRO_GT_CLOCK") and rank == 0:
+    if world > 1 and os.environ.get("HYDRO_BENCH_RANKS"):
+        print("rank %d: step %.2f ms, gs %.2f ms x %d, lu %.2f ms x %d" % (rank, h.event_elapsed_ms(0, 1) / K, gs_ms / max(gs_n, 1), gs_n, lu_ms / max(lu_n, 1), lu_n), file=sys.stderr)
+    if os.environ.get("HYDRO_GT_CLOCK"):
         # instrumented build (-DGT_CLOCK): cycles per warp role, summed over warps: producer store+publish / poll+load /
         # barrier wait; sweep warps barrier wait / step
-        print("gt_clocks", h.profile_read_clocks()[:8], "launches", gs_n, file=sys.stderr)
+        # [0] sweep warps: steps, [1] their barrier waits, [2] interface waits (slabs), [3] producers: dependency polls, [4] loads (incl.
+        # ghost planes), [5] barrier waits, [6] task time (one thread per task), [7] tasks
+        print("gt_clocks rank %d" % rank, h.profile_read_clocks()[:8], "launches", gs_n, "gs_ms", gs_ms / max(gs_n, 1), file=sys.stderr)
     clocks = sampler.stop() if sampler else None
     sec_step = ms * 1e-3 / K
     value = total_cells / sec_step

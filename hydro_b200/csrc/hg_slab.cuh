@@ -162,6 +162,14 @@ DV double ll_wait(const uint4* p, unsigned tag, unsigned long long* err) {
   }
   return __longlong_as_double((long long)(((unsigned long long)y << 32) | x));
 }
+// one (non-blocking) look at an entry: issue several, then check them -- a batch costs one memory latency
+DV uint4 ll_load(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+DV bool ll_ok(const uint4& v, unsigned tag) { return v.y == tag && v.w == tag; }
+DV double ll_value(const uint4& v) { return __longlong_as_double((long long)(((unsigned long long)v.z << 32) | v.x)); }
 __global__ void k_ll_fill(uint4* p, long long n, unsigned tag) {   // value 0 with the given tag
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) p[t] = make_uint4(0u, tag, 0u, tag);

@@ -584,7 +584,8 @@ static int gt_launch(hg_state* s, int sb, int se, double omega) {
   int grid = std::min(pl->ntasks, s->num_sms * GT_CTAS_PER_SM);
   if (s->cfg.solver_ctas > 0) grid = std::min(grid, s->cfg.solver_ctas);   // ranks sharing a device (tests)
   a.link = slab_link(s, 0);
-  if (s->world > 1) k_gs_tiled<true><<<grid, GT_BLOCK, GT_SMEM_BYTES, s->st>>>(s->geo, a, s->tmco);
+  static const bool force_link = getenv("HYDRO_GT_FORCE_LINK") != nullptr;   // diagnostics: the slab instantiation on one GPU
+  if (s->world > 1 || force_link) k_gs_tiled<true><<<grid, GT_BLOCK, GT_SMEM_BYTES, s->st>>>(s->geo, a, s->tmco);
   else k_gs_tiled<false><<<grid, GT_BLOCK, GT_SMEM_BYTES, s->st>>>(s->geo, a, s->tmco);
   CK(cudaGetLastError());
   if (e0) { cudaEventRecord(e1, s->st); s->prof_ev[0].push_back({e0, e1}); }
