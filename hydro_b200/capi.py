@@ -20,7 +20,7 @@ _lib = None
 
 SYMBOLS = [
     "hg_config_defaults", "hg_create", "hg_destroy", "hg_last_error", "hg_num_cells", "hg_num_faces",
-    "hg_set_field", "hg_get_field", "hg_set_field_async", "hg_get_field_async", "hg_step", "hg_run", "hg_fluid_start_step", "hg_fluid_make_iteration",
+    "hg_set_field", "hg_get_field", "hg_set_field_async", "hg_get_field_async", "hg_step", "hg_step_begin", "hg_step_end", "hg_run", "hg_fluid_start_step", "hg_fluid_make_iteration",
     "hg_fluid_convergence_indicator", "hg_fluid_is_converged", "hg_last_residuals", "hg_fluid_finish_step",
     "hg_fluid_auto_time_step", "hg_set_time_step", "hg_advection_step", "hg_heat_step",
     "hg_update_properties", "hg_calc_stat", "hg_interp_grad", "hg_linear_solve", "hg_smooth_field",
@@ -54,6 +54,8 @@ def load_library():
     l.hg_set_field_async.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t]
     l.hg_get_field_async.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t]
     l.hg_step.argtypes = [C.c_void_p, C.POINTER(HgStepStats)]
+    l.hg_step_begin.argtypes = [C.c_void_p]
+    l.hg_step_end.argtypes = [C.c_void_p, C.POINTER(HgStepStats)]
     l.hg_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(HgStepStats)]
     for n in ("hg_fluid_start_step", "hg_fluid_make_iteration", "hg_fluid_finish_step", "hg_advection_step",
               "hg_heat_step", "hg_update_properties", "hg_device_synchronize"):
@@ -166,6 +168,15 @@ class Hydro:
     def step(self):
         st = HgStepStats()
         self._chk(self.l.hg_step(self.h, C.byref(st)))
+        return st
+
+    def step_begin(self):
+        """Queues one time step (hg_step_begin); step_end() waits for it.  Transfers queued in between overlap the step."""
+        self._chk(self.l.hg_step_begin(self.h))
+
+    def step_end(self):
+        st = HgStepStats()
+        self._chk(self.l.hg_step_end(self.h, C.byref(st)))
         return st
 
     def run(self, nsteps):

@@ -32,7 +32,7 @@ struct hg_state {
   // asynchronous field transfers (hg_set_field_async / hg_get_field_async): copy streams, staging / snapshot buffers per field
   cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
   std::map<int, double*> xfer_stage, xfer_snap;
-  std::map<int, cudaEvent_t> xfer_ev;
+  std::map<int, cudaEvent_t> xfer_ev, xfer_stage_ev;
   cudaEvent_t xfer_ev_tmp[2] = {nullptr, nullptr};   // ordering events of the asynchronous transfers (created once)
   int dim = 0, n[3] = {1, 1, 1};
   long long nc = 0, nf = 0, nsh = 0;
@@ -73,6 +73,7 @@ struct hg_state {
   double* resid = nullptr;    // per-iteration convergence indicators of the current step (device, 4096)
   double* scal = nullptr;     // device scalars: [0] resid, [1] auto dt, [2..] stat (36), then diffs
   int* flag = nullptr;        // [0] scratch NaN flag (immediate checks), [1] any-excluded flag, [4..11] deferred NaN flags of a step
+  bool step_pending = false; int step_nadv = 0;   // between hg_step_begin and hg_step_end
   bool defer = false;         // inside hg_step: NaN flags, solver status words, sweep counts and statistics are read once, at the end
   double* sorres = nullptr;   // per pressure solve of the step: {iter, diff} computed on the device (deferred mode)
   int nsolves = 0;
@@ -770,7 +771,10 @@ extern "C" int hg_update_properties(hg_handle s) {
 // dataflow kernels, last convergence indicator, deferred sweep counts) travels behind the 36 statistics values in the
 // same transfer / the same rank-ordered reduction, so a step waits for the device once.
 enum { ST_STAT = 2, ST_STATUS = 38, ST_TOTAL = 51 };   // offsets in s->scal / s->hscal
-static int calc_stat(hg_state* s, hg_step_stats* st, bool with_status) {
+static int calc_stat_finish(hg_state* s, hg_step_stats* st);
+// enqueue: statistics kernel + status block + transfer into the pinned mirror (slabs: the rank-ordered reduction, which waits);
+// calc_stat_finish waits for the stream and decodes
+static int calc_stat_enqueue(hg_state* s, bool with_status) {
   const hg_config& c = s->cfg;
   double init[36];
   for (int p = 0; p < 3; ++p) { for (int q = 0; q < 12; ++q) init[p * 12 + q] = 0.; init[p * 12 + 7] = 1e10; init[p * 12 + 8] = -1e10; }
@@ -802,8 +806,12 @@ static int calc_stat(hg_state* s, hg_step_stats* st, bool with_status) {
     }
   } else {
     CK(cudaMemcpyAsync(s->hscal + ST_STAT, s->scal + ST_STAT, nvals * sizeof(double), cudaMemcpyDeviceToHost, s->st));
-    CK(cudaStreamSynchronize(s->st));
   }
+  return 0;
+}
+static int calc_stat_finish(hg_state* s, hg_step_stats* st) {
+  const hg_config& c = s->cfg;
+  if (s->world == 1) CK(cudaStreamSynchronize(s->st));
   hg_step_stats& o = s->stat;
   for (int p = 0; p < c.num_phases; ++p) {
     const double* r = s->hscal + ST_STAT + p * 12;
@@ -821,6 +829,10 @@ static int calc_stat(hg_state* s, hg_step_stats* st, bool with_status) {
     }
   }
   return 0;
+}
+static int calc_stat(hg_state* s, hg_step_stats* st, bool with_status) {
+  if (int rc = calc_stat_enqueue(s, with_status)) return rc;
+  return calc_stat_finish(s, st);
 }
 extern "C" int hg_calc_stat(hg_handle s, hg_step_stats* st) {
   if (!s) return HG_ERR_INVALID;
@@ -1188,10 +1200,14 @@ static int step_body(hg_state* s, int* nadv_out) {
   if (c.heat_enable) { tpush(s, "step.heat"); if ((rc = hg_heat_step(s))) return rc; tpop(s); }
   if ((rc = hg_update_properties(s))) return rc;
   *nadv_out = nadv;
-  return calc_stat(s, nullptr, true);
+  return calc_stat_enqueue(s, true);
 }
-extern "C" int hg_step(hg_handle s, hg_step_stats* stats) {   // hydro2d.hpp:1531-1621
+// hydro<Mesh>::step() (hydro2d.hpp:1531-1621) in two halves: hg_step_begin enqueues the whole step (it only waits where the
+// control flow needs a device result: stop tests with a tolerance, dt_auto, slab reductions), hg_step_end waits for the status
+// block and decodes it.  Between the two the caller can queue the transfers of the next step (hg_set_field_async).
+extern "C" int hg_step_begin(hg_handle s) {
   if (!s) return HG_ERR_INVALID;
+  if (s->step_pending) { s->err = "hg_step_begin: the previous step has not been ended (hg_step_end)"; return HG_ERR_INVALID; }
   cudaSetDevice(s->dev);
   const size_t tdepth = s->timer_stack.size();
   tpush(s, "step");
@@ -1200,11 +1216,20 @@ extern "C" int hg_step(hg_handle s, hg_step_stats* stats) {   // hydro2d.hpp:153
   // end: NaN flags, solver status words, sweep counts and statistics come back in one block
   s->defer = true;
   CK(cudaMemsetAsync(s->flag + 4, 0, NF_COUNT * sizeof(int), s->st));
-  int nadv = 0;
-  int rc = step_body(s, &nadv);
+  s->step_nadv = 0;
+  const int rc = step_body(s, &s->step_nadv);
   s->defer = false;
   while (s->timer_stack.size() > tdepth) tpop(s);   // also on error paths
   if (rc) return rc;
+  s->step_pending = true;
+  return 0;
+}
+extern "C" int hg_step_end(hg_handle s, hg_step_stats* stats) {
+  if (!s) return HG_ERR_INVALID;
+  if (!s->step_pending) { s->err = "hg_step_end without hg_step_begin"; return HG_ERR_INVALID; }
+  cudaSetDevice(s->dev);
+  s->step_pending = false;
+  if (int rc = calc_stat_finish(s, nullptr)) return rc;
   const double* sb = s->hscal + ST_STATUS;
   if (sb[8] != 0.) { s->err = "k_gs_tiled: dependency wait timed out"; return HG_ERR_CUDA; }
   if (sb[9] != 0.) { s->err = "k_lu_tiled: dependency wait timed out"; return HG_ERR_CUDA; }
@@ -1216,10 +1241,14 @@ extern "C" int hg_step(hg_handle s, hg_step_stats* stats) {   // hydro2d.hpp:153
   s->stat.convergence_indicator = s->iter_count > 0 ? sb[10] : 1.;
   s->stat.pressure_sweeps_total = s->sweeps_total;
   s->stat.pressure_last_diff = s->last_diff;
-  s->stat.advection_substeps = nadv;
+  s->stat.advection_substeps = s->step_nadv;
   s->stat.dt = s->dt; s->stat.time = s->time_fluid;
   if (stats) *stats = s->stat;
   return 0;
+}
+extern "C" int hg_step(hg_handle s, hg_step_stats* stats) {
+  if (int rc = hg_step_begin(s)) return rc;
+  return hg_step_end(s, stats);
 }
 
 extern "C" int hg_run(hg_handle s, int nsteps, hg_step_stats* last) {
@@ -1709,6 +1738,7 @@ extern "C" int hg_destroy(hg_handle s) {
   if (s->st_h2d) cudaStreamDestroy(s->st_h2d);
   if (s->st_d2h) cudaStreamDestroy(s->st_d2h);
   for (auto& e : s->xfer_ev) cudaEventDestroy(e.second);
+  for (auto& e : s->xfer_stage_ev) cudaEventDestroy(e.second);
   delete s;
   return 0;
 }
@@ -1800,15 +1830,24 @@ extern "C" int hg_set_field_async(hg_handle s, int field, const double* src, siz
   if (!p || (long long)n != m || field == HG_F_EXCLUDED) { s->err = "hg_set_field_async: bad field id or size"; return HG_ERR_INVALID; }
   double* stage = nullptr;
   if (int rc = xfer_setup(s, field, m, s->xfer_stage, &stage)) return rc;
-  // (an event can be re-recorded once the wait on its previous record has been enqueued)
-  CK(cudaEventRecord(s->xfer_ev_tmp[0], s->st)); CK(cudaStreamWaitEvent(s->st_h2d, s->xfer_ev_tmp[0], 0));   // the staging buffer's last consumer is done
+  // the staging buffer is free once the compute stream has applied its previous contents (an event recorded right after that
+  // copy, NOT the end of everything queued since: the upload of the next step's fields overlaps the running step)
+  auto ev = s->xfer_stage_ev.find(field);
+  if (ev == s->xfer_stage_ev.end()) {
+    cudaEvent_t e = nullptr; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ev = s->xfer_stage_ev.emplace(field, e).first;
+  } else {
+    CK(cudaStreamWaitEvent(s->st_h2d, ev->second, 0));
+  }
   CK(cudaMemcpyAsync(stage, src, n * sizeof(double), cudaMemcpyHostToDevice, s->st_h2d));
+  // (an event can be re-recorded once the wait on its previous record has been enqueued)
   CK(cudaEventRecord(s->xfer_ev_tmp[1], s->st_h2d)); CK(cudaStreamWaitEvent(s->st, s->xfer_ev_tmp[1], 0));
   CK(cudaMemcpyAsync(p, stage, n * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
   if (field <= HG_F_TEMPERATURE) {
     double* q = field_ptr(s, field, L_TP, &m);
     CK(cudaMemcpyAsync(q, stage, n * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
   }
+  CK(cudaEventRecord(ev->second, s->st));
   return 0;
 }
 extern "C" int hg_get_field_async(hg_handle s, int field, double* dst, size_t n) {

@@ -199,6 +199,14 @@ int hg_get_field_async(hg_handle h, int field, double* dst, size_t n);
 
 /* one whole time step = hydro<Mesh>::step() (hydro2d.hpp:1531-1621) */
 int hg_step(hg_handle h, hg_step_stats* stats /* may be NULL */);
+/* the same step in two halves (hg_step = hg_step_begin + hg_step_end): hg_step_begin queues the step on the device and
+ * returns, hg_step_end waits for its status block (NaN flags, solver status, statistics) and fills `stats`.  Between the two a
+ * caller can queue the transfers of the NEXT step (hg_set_field_async: the upload runs on the copy stream while the step
+ * computes and is applied in stream order after it) -- the module-owned property fields of hydro<Mesh> (hydro2d.hpp:449-463)
+ * no longer cost their PCIe time.  hg_step_begin still waits where the reference's control flow needs a device result (see
+ * hg_run).  Errors of the step are reported by hg_step_end. */
+int hg_step_begin(hg_handle h);
+int hg_step_end(hg_handle h, hg_step_stats* stats /* may be NULL */);
 /* n steps back to back.  The host only waits for the device where the reference's control flow depends on
  * device results: once per step (NaN flags, solver status words, statistics, all in one pinned status block),
  * plus once per SIMPLE iteration when convergence_tolerance > 0 and once per chunk of pressure sweeps when
