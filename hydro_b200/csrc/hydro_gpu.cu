@@ -61,6 +61,7 @@ struct hg_state {
   GtPlan gt_plans[GT_PLAN_SLOTS];
   int gt_plan_cap = 0; long long gt_plan_clock = 0;
   int* gt_ctl = nullptr;
+  std::vector<int> sor_pred = std::vector<int>(256, -1);   // stopping sweep of the pressure solve of SIMPLE iteration q in the previous step
   int gt_gbase = 0;                           // sweep groups of the current solve launched so far (parity of the slabs' "down" planes)
   unsigned long long* gt_clk = nullptr;
   // lu as a dataflow of column boxes (hg_lu_tiled.cuh)
@@ -379,9 +380,21 @@ static int run_sor(hg_state* s, double* x, long long nx_, double tol, int limit,
   }
   int chunk = s->cfg.pressure_sweeps_per_check > 0 ? s->cfg.pressure_sweeps_per_check : 128;
   if (chunk > SOLVER_SC) chunk = SOLVER_SC;
+  // The stopping sweep is only known after the fact, and a chunk that runs past it is replayed from its checkpoint with the
+  // exact count: a fixed chunk of 128 sweeps executes up to twice the sweeps the reference does.  The stopping sweep of the
+  // same SIMPLE iteration of the previous time step is a good predictor (the system changes slowly): the first chunk ends a
+  // few sweeps before it, then short chunks (doubling) follow -- the replay costs a few sweeps.  Without a prediction: `chunk`.
+  const int pidx = std::min(std::max(s->iter_count, 0), (int)s->sor_pred.size() - 1);
+  const int pred = s->sor_pred[pidx];
+  int small = 8;
   int done = 0;
   while (done < max_total) {
-    int n = std::min(chunk, max_total - done);
+    int n = chunk;
+    if (pred >= 0) {
+      if (done == 0 && pred + 1 - 4 >= small) n = std::min(chunk, pred + 1 - 4);
+      else { n = std::min(chunk, small); small *= 2; }
+    }
+    n = std::min(n, max_total - done);
     CK(cudaMemcpyAsync(s->PPsave, x, nx_ * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
     const int gbase_save = s->gt_gbase;
     if (s->world > 1) {
@@ -405,11 +418,13 @@ static int run_sor(hg_state* s, double* x, long long nx_, double tol, int limit,
         if (int rc = launch(done, stop + 1)) return rc;
       }
       *out_iter = stop; *out_diff = s->hdiffs[stop];
+      s->sor_pred[pidx] = stop;
       return 0;
     }
     done += n;
   }
   *out_iter = limit + 1; *out_diff = s->hdiffs[max_total - 1];
+  s->sor_pred[pidx] = max_total - 1;
   return 0;
 }
 
