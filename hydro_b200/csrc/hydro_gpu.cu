@@ -765,8 +765,10 @@ extern "C" int hg_update_properties(hg_handle s) {
   LAUNCH(s, k_force, nblk(s->nc), 256, s->dim, s->rho_raw, c.gravity[0], c.gravity[1], c.gravity[2], c.force[0], c.force[1],
          c.force[2], p3(s->force), s->nc);
   if (c.num_phases >= 2 && c.sigma != 0.) {
+    XCH(s, 1, s->vf[1]);   // slabs: the volume fraction and then its gradient across the interfaces
     P3 gs; for (int d = 0; d < 3; ++d) gs.p[d] = s->G[d];
     DIMSEL(s, k_grad_pd, nblk(s->nc), 256, s->geo, s->vf[1], s->pd_init[0], gs);
+    XCH(s, 1, s->G[0], s->G[1], s->dim > 2 ? s->G[2] : nullptr);
     CP3 gsc; for (int d = 0; d < 3; ++d) gsc.p[d] = s->G[d];
     DIMSEL(s, k_stforce, nblk(s->nc), 256, s->geo, gsc, c.sigma, p3(s->stforce));
   }
@@ -777,7 +779,7 @@ extern "C" int hg_update_properties(hg_handle s) {
     }
   }
   // slabs: face values of density, viscosity and force are taken across the slab interfaces
-  XCH(s, 1, s->rho, s->mu, s->force[0], s->force[1], s->dim > 2 ? s->force[2] : nullptr);
+  XCH(s, 1, s->rho, s->mu, s->force[0], s->force[1], s->dim > 2 ? s->force[2] : nullptr, c.heat_enable ? s->kc : nullptr);
   tpop(s);
   return 0;
 }
@@ -1158,12 +1160,14 @@ extern "C" int hg_heat_step(hg_handle s) {   // heat.hpp:69-84 + conv_diff.hpp:1
   cudaSetDevice(s->dev);
   const hg_config& c = s->cfg;
   if (int rc = check_nan(s, s->T[L_TC], s->nc, NF_HEAT_INIT)) return rc;
+  XCH(s, 1, s->T[L_TC]);   // slabs: face values of the temperature across the interfaces
   const unsigned gb = nblk(s->nc);
   // gradient of the temperature for the deferred upwind correction (conv_diff.hpp:135)
   P3 g3; for (int d = 0; d < 3; ++d) g3.p[d] = s->G[d];
   if (s->dim == 3) { k_interp_grad<3, K_TEMP><<<gb, 256, 0, s->st>>>(s->geo, s->T[L_TC], 0, g3); }
   else { k_interp_grad<2, K_TEMP><<<gb, 256, 0, s->st>>>(s->geo, s->T[L_TC], 0, g3); }
   ++s->launches;
+  XCH(s, 1, s->G[0], s->G[1], s->dim > 2 ? s->G[2] : nullptr);   // gradients of the upwind cells across the interfaces
   AsmArgs a;
   for (int n = 0; n < 3; ++n) { a.prev[n] = s->T[L_TC]; a.tc[n] = s->T[L_TC]; a.tp[n] = s->T[L_TP]; a.src[n] = s->zero; a.R[n] = s->R[n]; }
   for (int q = 0; q < 9; ++q) a.grad[q] = s->G[q % 3];
@@ -1375,8 +1379,6 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     return fail_create(nullptr, HG_ERR_INVALID, "z-slab decomposition needs dim 3 and at least 2 planes per rank");
   if (cfg->world_size > 1 && (cfg->linear_solver_pressure == HG_LS_LU_RELAXED || cfg->linear_solver_pressure == HG_LS_JACOBI))
     return fail_create(nullptr, HG_ERR_INVALID, "multi-GPU slabs support gauss_seidel for the pressure system");
-  if (cfg->world_size > 1 && (cfg->heat_enable || (cfg->num_phases >= 2 && cfg->sigma != 0.)))
-    return fail_create(nullptr, HG_ERR_INVALID, "multi-GPU slabs: heat_enable / surface tension are not decomposed yet");
   if (cfg->world_size > SLAB_MAX_WORLD) return fail_create(nullptr, HG_ERR_INVALID, "world_size too large");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)

@@ -16,11 +16,11 @@ FIELDS = ["VELOCITY_X", "VELOCITY_Y", "VELOCITY_Z", "PRESSURE", "VOLUME_FLUX", "
           "DENSITY", "VISCOSITY", "FORCE_Y"]
 
 
-def single(p, nsteps):
+def single(p, nsteps, fields=None):
     from hydro_b200.capi import Hydro
     h = Hydro(p)
     st = [h.step() for _ in range(nsteps)][-1]
-    out = {n: h.get(n) for n in FIELDS}
+    out = {n: h.get(n) for n in (fields or FIELDS)}
     h.close()
     return st, out
 
@@ -32,7 +32,8 @@ def devices_for(world):
 
 
 @pytest.mark.parametrize("kernel", ["hyperplane", "tiled"])
-@pytest.mark.parametrize("case,world", [("rt3d_16", 2), ("rt3d_20x12x17", 3), ("dam3d_32x10x12", 2), ("rt3d_tol", 2)])
+@pytest.mark.parametrize("case,world", [("rt3d_16", 2), ("rt3d_20x12x17", 3), ("dam3d_32x10x12", 2), ("rt3d_tol", 2),
+                                        ("rt3d_stf_20x12x16", 2), ("thermal3d_24x12x15", 3)])
 def test_slabs_equal_single_gpu(case, world, kernel, monkeypatch):
     # hyperplane: the neighbour-linked hyperplane kernels on both sides; tiled: the box-dataflow kernels (k_gs_tiled,
     # k_lu_tiled) with tagged interface values between the slabs -- all bitwise equal to the single-GPU run
@@ -42,16 +43,22 @@ def test_slabs_equal_single_gpu(case, world, kernel, monkeypatch):
     p = {"rt3d_16": cases.rt3d(16),
          "rt3d_20x12x17": cases.rt3d(8, Nx=20, Ny=12, Nz=17, lu_relaxed_num_iters_limit=30),
          "dam3d_32x10x12": cases.broken_dam_3d(32, 10, 12, lu_relaxed_num_iters_limit=40),
+         # surface tension (CalcForce, hydro2d.hpp:1318-1370) and the temperature equation (heat.hpp:19-93) on slabs
+         "rt3d_stf_20x12x16": cases.rt3d(8, Nx=20, Ny=12, Nz=16, lu_relaxed_num_iters_limit=20, sigma=0.07, tvd_split=1),
+         "thermal3d_24x12x15": cases.rt3d(8, Nx=24, Ny=12, Nz=15, lu_relaxed_num_iters_limit=15, heat_enable=1,
+                                          heat_box_lb=(-1., -1., -1.), heat_box_rt=(2., 0.01, 2.), heat_box_temperature=1.,
+                                          conductivity_0=0.01, conductivity_1=0.05),
          "rt3d_tol": cases.rt3d(12, fixed_work=False, lu_relaxed_num_iters_limit=200, lu_relaxed_tolerance=1e-6,
                                num_iterations_limit=3, pressure_sweeps_per_check=32)}[case]
-    st1, f1 = single(p, 2)
+    fields = FIELDS + (["TEMPERATURE"] if p.get("heat_enable") else []) + (["STFORCE_X", "STFORCE_Y", "STFORCE_Z"] if p.get("sigma") else [])
+    st1, f1 = single(p, 2, fields)
     devs, ctas = devices_for(world)
-    stn, fn = parallel.run_local_ranks(p, world, 2, FIELDS, devices=devs, solver_ctas=ctas)
+    stn, fn = parallel.run_local_ranks(p, world, 2, fields, devices=devs, solver_ctas=ctas)
     assert stn.simple_iterations == st1.simple_iterations
     assert stn.pressure_sweeps_total == st1.pressure_sweeps_total
     assert stn.pressure_last_diff == st1.pressure_last_diff
     assert stn.convergence_indicator == st1.convergence_indicator
-    for n in FIELDS:
+    for n in fields:
         assert np.array_equal(fn[n], f1[n]), n
     for ph in range(2):
         assert abs(stn.volume[ph] - st1.volume[ph]) <= 1e-12 * abs(st1.volume[ph])
