@@ -352,20 +352,26 @@ __global__ void __launch_bounds__(256, 4) k_prhs_co5(Geo g, const double* __rest
 
 // ------------------------------------------------------------------------------------------------ K_correct
 __global__ void __launch_bounds__(FT_THREADS, 4) k_fd_correct(Geo g, const unsigned char* __restrict__ slow, CorrArgs a) {
+  __shared__ double smax[FT_K];
   FT_PROLOG(g)
-  if (!in) return;
+  if (in) {
 #pragma unroll
-  for (int d = 0; d < 3; ++d) { ft_prefetch(a.u[d] + c); ft_prefetch(a.Fs + fidx(g, d, i, j, k)); }
-  ft_prefetch(a.pc + c); ft_prefetch(a.dc + c);
-  if (slow[c]) return;
+    for (int d = 0; d < 3; ++d) { ft_prefetch(a.u[d] + c); ft_prefetch(a.Fs + fidx(g, d, i, j, k)); if (a.resid) ft_prefetch(a.uprev[d] + c); }
+    ft_prefetch(a.pc + c); ft_prefetch(a.dc + c);
+  }
+  double rs = 0.;   // |u_prev - u_new| of this cell (CalcDiff, solver.hpp:804-813)
+  if (in && !slow[c]) {
   const HgDiv dvol = hg_div_prepare(g.vol);
   const long long off[3] = {1, g.sy, g.sz};
   const double pcc = a.pc[c], dcc = a.dc[c];
+  double sq = 0.;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const double pm = a.pc[c - off[d]], pp = a.pc[c + off[d]];
     const double gpc = ft_grad(pm, pcc, pp, g.area[d] * -1., g.area[d] * 1., dvol);
-    a.u[d][c] += gpc / (-dcc);
+    const double un = a.u[d][c] + gpc / (-dcc);
+    a.u[d][c] = un;
+    if (a.resid) { const double e = a.uprev[d][c] - un; sq += e * e; }
     // minus face: F = F* + c_f (p'_m - p'_p) (fluid.hpp:1053-1056)
     const long long fx = fidx(g, d, i, j, k);
     double r = a.Fs[fx];
@@ -384,6 +390,20 @@ __global__ void __launch_bounds__(FT_THREADS, 4) k_fd_correct(Geo g, const unsig
       rp += pcc * cfp;
       rp += pp * (-cfp);
       a.F[fp_] = rp;
+    }
+  }
+  rs = sqrt(sq);
+  if (!(rs == rs)) rs = 0.;   // std::max(res, NaN) keeps res
+  }
+  if (a.resid) {
+    rs = warp_max(rs);
+    if (tx == 0) smax[ty] = rs;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double m = smax[0];
+#pragma unroll
+      for (int q = 1; q < FT_K; ++q) m = m < smax[q] ? smax[q] : m;
+      if (m > 0.) atomic_max_nonneg(a.resid, m);
     }
   }
 }

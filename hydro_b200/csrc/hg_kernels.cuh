@@ -42,10 +42,38 @@ __global__ void k_fill(double* a, double v, long long n) {
 }
 // StartStep: iter_curr = time_curr + (time_curr - time_prev) * guess_extrapolation
 // (fluid.hpp:800-811, conv_diff.hpp:123-128)
+// nanflag != nullptr: also the IsNan scan of time_curr (solver.hpp:17-30, fluid.hpp:795-799) over the first n_scan entries
 __global__ void k_start_layer(double* __restrict__ ic, const double* __restrict__ tc,
-                              const double* __restrict__ tp, double ge, long long n) {
+                              const double* __restrict__ tp, double ge, long long n, int* nanflag = nullptr, long long n_scan = 0) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) ic[t] = tc[t] + (tc[t] - tp[t]) * ge;
+  if (t < n) {
+    const double v = tc[t];
+    ic[t] = v + (v - tp[t]) * ge;
+    if (nanflag && t < n_scan && !(v * 0. == 0.)) *nanflag = 1;
+  }
+}
+// IsNan scans of up to four arrays in one pass
+struct Nan4 { const double* a[4]; int* flag[4]; int n; };
+__global__ void k_nan_flag4(Nan4 q, long long n) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) if (m < q.n && !(q.a[m][t] * 0. == 0.)) *q.flag[m] = 1;
+}
+// CalcDiff over a cell list (the shell of the interior kernels)
+__global__ void k_resid_list(Geo g, CP3 ic, CP3 ip, double* out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.;
+  if (t < g.ncells) {
+    const long long c = g.cells[t];
+    double sq = 0.;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { const double e = ip.p[d][c] - ic.p[d][c]; sq += e * e; }
+    v = sqrt(sq);
+    if (!(v == v)) v = 0.;
+  }
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0 && v > 0.) atomic_max_nonneg(out, v);
 }
 __global__ void k_flag_to_double(const int* flag, double* out) { *out = *flag ? 1. : 0.; }
 // IsNan scan (solver.hpp:17-30): sets *flag when !(a*0 == 0)
@@ -544,7 +572,8 @@ __global__ void k_pcorr(Geo g, const double* __restrict__ PP, const double* __re
 
 // K_correct: velocity correction u += -grad p' / d_c (fluid.hpp:1040-1050) and the divergence-free
 // fluxes F = F* + c_f (p'_m - p'_p) (fluid.hpp:1053-1056)
-struct CorrArgs { const double* pc; const double* dc; const double* Fs; double* u[3]; double* F; };
+struct CorrArgs { const double* pc; const double* dc; const double* Fs; double* u[3]; double* F;
+                  const double* uprev[3]; double* resid; };   // interior kernel: max_c |u_prev - u_new| (CalcDiff), nullable
 template <int DIM, bool INT = false>
 DV double fcorr_face(const Geo& g, const CorrArgs& a, int d, int fi, int fj, int fk) {
   const long long fx = fidx(g, d, fi, fj, fk);

@@ -893,13 +893,20 @@ extern "C" int hg_fluid_start_step(hg_handle s) {   // fluid.hpp:793-812
   CK(cudaMemsetAsync(s->resid, 0, 4096 * sizeof(double), s->st));
   // slabs: the caller may have set density / viscosity / force since the last hg_update_properties
   XCH(s, 1, s->rho, s->mu, s->force[0], s->force[1], s->dim > 2 ? s->force[2] : nullptr);
-  if (int rc = check_nan(s, s->p[L_TC], s->nc, NF_INIT_P)) return rc;
   const double ge = s->cfg.guess_extrapolation;
-  for (int d = 0; d < s->dim; ++d) {
-    if (int rc = check_nan(s, s->u[L_TC][d], s->nc, NF_INIT_U)) return rc;
-    LAUNCH(s, k_start_layer, nblk(s->nc), 256, s->u[L_IC][d], s->u[L_TC][d], s->u[L_TP][d], ge, s->nc);
+  if (s->defer) {
+    // inside hg_step the IsNan scans of time_curr ride on the pass that reads it anyway (flags read at the end of the step)
+    for (int d = 0; d < s->dim; ++d)
+      LAUNCH(s, k_start_layer, nblk(s->nc), 256, s->u[L_IC][d], s->u[L_TC][d], s->u[L_TP][d], ge, s->nc, s->flag + 4 + NF_INIT_U, s->nc);
+    LAUNCH(s, k_start_layer, nblk(s->nc), 256, s->p[L_IC], s->p[L_TC], s->p[L_TP], ge, s->nc, s->flag + 4 + NF_INIT_P, s->nc);
+  } else {
+    if (int rc = check_nan(s, s->p[L_TC], s->nc, NF_INIT_P)) return rc;
+    for (int d = 0; d < s->dim; ++d) {
+      if (int rc = check_nan(s, s->u[L_TC][d], s->nc, NF_INIT_U)) return rc;
+      LAUNCH(s, k_start_layer, nblk(s->nc), 256, s->u[L_IC][d], s->u[L_TC][d], s->u[L_TP][d], ge, s->nc);
+    }
+    LAUNCH(s, k_start_layer, nblk(s->nc), 256, s->p[L_IC], s->p[L_TC], s->p[L_TP], ge, s->nc);
   }
-  LAUNCH(s, k_start_layer, nblk(s->nc), 256, s->p[L_IC], s->p[L_TC], s->p[L_TP], ge, s->nc);
   LAUNCH(s, k_start_layer, nblk(s->nf), 256, s->F[L_IC], s->F[L_TC], s->F[L_TP], ge, s->nf);
   return 0;
 }
@@ -1055,19 +1062,27 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
   tpop(s);
   XCH(s, 1, s->pc);
   tpush(s, "fluid.7.correction");
-  { CorrArgs a; a.pc = s->pc; a.dc = s->dc; a.Fs = s->Fs; a.F = s->F[L_IC];
-    for (int d = 0; d < 3; ++d) a.u[d] = s->u[L_IC][d];
-    if (fast) {
-      k_fd_correct<<<fg, FT_THREADS, 0, s->st>>>(s->geo, s->slow, a); ++s->launches;
-      if (s->nslow) { k_correct<3><<<gbl, 256, 0, s->st>>>(gl, a); ++s->launches; }
-    } else DIMSEL(s, k_correct, gb, 256, s->geo, a); }
-  tpop(s);
   // convergence indicator (fluid.hpp:174-179): computed now into resid[iteration], fetched lazily
   double* rdst = s->resid + (s->iter_count < 4096 ? s->iter_count : 4095);
   if (s->iter_count >= 4095) CK(cudaMemsetAsync(rdst, 0, sizeof(double), s->st));
-  if (s->dim == 3) { k_resid<3><<<gb, 256, 0, s->st>>>(cp3(s->u[L_IC]), cp3(s->u[L_IP]), s->nc, rdst); }
-  else { k_resid<2><<<gb, 256, 0, s->st>>>(cp3(s->u[L_IC]), cp3(s->u[L_IP]), s->nc, rdst); }
-  ++s->launches;
+  { CorrArgs a; a.pc = s->pc; a.dc = s->dc; a.Fs = s->Fs; a.F = s->F[L_IC];
+    for (int d = 0; d < 3; ++d) { a.u[d] = s->u[L_IC][d]; a.uprev[d] = s->u[L_IP][d]; }
+    a.resid = nullptr;
+    if (fast) {
+      a.resid = rdst;   // interior cells: the maximum is taken where the new velocity is formed; the shell has its own pass
+      k_fd_correct<<<fg, FT_THREADS, 0, s->st>>>(s->geo, s->slow, a); ++s->launches;
+      if (s->nslow) {
+        a.resid = nullptr;
+        k_correct<3><<<gbl, 256, 0, s->st>>>(gl, a); ++s->launches;
+        k_resid_list<<<gbl, 256, 0, s->st>>>(gl, cp3(s->u[L_IC]), cp3(s->u[L_IP]), rdst); ++s->launches;
+      }
+    } else DIMSEL(s, k_correct, gb, 256, s->geo, a); }
+  tpop(s);
+  if (!fast) {
+    if (s->dim == 3) { k_resid<3><<<gb, 256, 0, s->st>>>(cp3(s->u[L_IC]), cp3(s->u[L_IP]), s->nc, rdst); }
+    else { k_resid<2><<<gb, 256, 0, s->st>>>(cp3(s->u[L_IC]), cp3(s->u[L_IP]), s->nc, rdst); }
+    ++s->launches;
+  }
   ++s->iter_count;
   s->last_resid = -1.;   // not fetched yet
   return 0;
@@ -1103,8 +1118,15 @@ extern "C" int hg_fluid_finish_step(hg_handle s) {   // fluid.hpp:1159-1169, con
   rot(s->p[L_TC], s->p[L_TP], s->p[L_IC]);
   rot(s->F[L_TC], s->F[L_TP], s->F[L_IC]);
   for (int d = 0; d < s->dim; ++d) rot(s->u[L_TC][d], s->u[L_TP][d], s->u[L_IC][d]);
-  if (int rc = check_nan(s, s->p[L_TC], s->nc, NF_FIN_P)) return rc;
-  for (int d = 0; d < s->dim; ++d) if (int rc = check_nan(s, s->u[L_TC][d], s->nc, NF_FIN_U)) return rc;
+  if (s->defer) {   // one pass over the four arrays, flags read at the end of the step
+    Nan4 q; q.n = 1 + s->dim;
+    q.a[0] = s->p[L_TC]; q.flag[0] = s->flag + 4 + NF_FIN_P;
+    for (int d = 0; d < 3; ++d) { q.a[1 + d] = d < s->dim ? s->u[L_TC][d] : s->p[L_TC]; q.flag[1 + d] = s->flag + 4 + NF_FIN_U; }
+    LAUNCH(s, k_nan_flag4, nblk(s->nc), 256, q, s->nc);
+  } else {
+    if (int rc = check_nan(s, s->p[L_TC], s->nc, NF_FIN_P)) return rc;
+    for (int d = 0; d < s->dim; ++d) if (int rc = check_nan(s, s->u[L_TC][d], s->nc, NF_FIN_U)) return rc;
+  }
   s->time_fluid += s->dt;
   return 0;
 }
