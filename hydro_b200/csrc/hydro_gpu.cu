@@ -618,6 +618,7 @@ static int gt_check(hg_state* s) {   // after the sweeps: did a dependency wait 
 }
 
 static int lt_check(hg_state* s);
+static int solve_system(hg_state* s, int solver, double* R, double* X, double* t1, double* t2, int* it, double* df);
 static void launch_pcorr(hg_state* s) {   // p' back to the natural layout, p_curr = p_prev + alpha p'
   const double alpha = s->cfg.pressure_relaxation_factor;
   if (s->dim == 3) k_ft_pcorr<<<fast_grid(s), FT_THREADS, 0, s->st>>>(s->geo, s->PP, s->p[L_IP], alpha, s->pc, s->p[L_IC]);
@@ -665,9 +666,18 @@ static int solve_pressure(hg_state* s) {
     if (int rc = run_lu_relaxed(s, s->RP, s->PP, s->X[0], s->X[1], c.lu_relaxed_tolerance, c.lu_relaxed_num_iters_limit,
                                 c.lu_relaxed_relaxation_factor, &it, &df)) return rc;
     launch_pcorr(s);
-  } else {
-    s->err = "linear_solver_pressure: lu is not iterated for the pressure system on the GPU path";
-    return HG_ERR_INVALID;
+  } else {   // lu: one forward + backward sweep over the explicit rows (linear.hpp:533-566); the factory reports no sweeps
+    P7 rows;
+    if (s->dim == 3) {
+      for (int t = 0; t < 7; ++t) rows.p[t] = s->An[t];
+      DIMSEL(s, k_prows, nblk(s->nc), 256, s->geo, s->dc, 0, rows);
+      shear_arrays(s, s->An, s->A, 7);
+    } else {
+      for (int t = 0; t < 7; ++t) rows.p[t] = s->A[t];
+      DIMSEL(s, k_prows, nblk(s->nc), 256, s->geo, s->dc, 1, rows);
+    }
+    if (int rc = solve_system(s, HG_LS_LU, s->RP, s->PP, nullptr, nullptr, &it, &df)) return rc;
+    launch_pcorr(s);
   }
   if (!s->defer && s->lu_tiled) if (int rc = lt_check(s)) return rc;   // the momentum solve's dataflow kernel
   if (it < 0) ++s->nsolves;   // deferred: counted on the device, added at the end of the step
@@ -685,10 +695,10 @@ static int shear_arrays(hg_state* s, double* const* in, double* const* out, int 
   return 0;
 }
 
-static int solve_lu_tiled(hg_state* s, int ncomp) {
+static int solve_lu_tiled(hg_state* s, int ncomp, double* const* Rs = nullptr, double* const* Xs = nullptr) {
   LtArgs a{};
   for (int t = 0; t < 7; ++t) a.A[t] = s->A[t];
-  for (int n = 0; n < 3; ++n) { a.R[n] = s->R[n]; a.X[n] = s->X[n]; }
+  for (int n = 0; n < 3; ++n) { a.R[n] = Rs && n < ncomp ? Rs[n] : s->R[n]; a.X[n] = Xs && n < ncomp ? Xs[n] : s->X[n]; }
   a.ncomp = ncomp; a.boxes = s->lt_boxes; a.nboxes = s->lt_nboxes; a.nbi = s->lt_nbi; a.progress = s->lt_progress; a.ctl = s->lt_ctl;
   if (s->world > 1) ++s->slab.lu_seq;
   a.link = slab_link(s, 1); a.link_stride = s->nxy;
@@ -720,17 +730,52 @@ static int lt_check(hg_state* s) {   // did a dependency wait time out?
   return 0;
 }
 
-static int solve_lu(hg_state* s, int ncomp) {
-  if (s->lu_tiled) return solve_lu_tiled(s, ncomp);
+static int solve_lu(hg_state* s, int ncomp, double* const* Rs = nullptr, double* const* Xs = nullptr) {
+  if (s->lu_tiled) return solve_lu_tiled(s, ncomp, Rs, Xs);
   LuArgs a{};
   for (int t = 0; t < 7; ++t) a.A[t] = s->A[t];
-  for (int n = 0; n < 3; ++n) { a.R[n] = s->R[n]; a.X[n] = s->X[n]; }
+  for (int n = 0; n < 3; ++n) { a.R[n] = Rs && n < ncomp ? Rs[n] : s->R[n]; a.X[n] = Xs && n < ncomp ? Xs[n] : s->X[n]; }
   a.ncomp = ncomp; a.tt = s->tt;
   if (s->world > 1) ++s->slab.lu_seq;
   a.link = slab_link(s, 1); a.link_stride = s->nxy;
   if (s->dim == 3 && s->world > 1) return coop_launch(s, k_lu_persistent<3, true>, s->grid_lu, s->geo, a, 1);
   if (s->dim == 3) return coop_launch(s, k_lu_persistent<3>, s->grid_lu, s->geo, a, 1);
   return coop_launch(s, k_lu_persistent<2>, s->grid_lu, s->geo, a, 1);
+}
+
+// One system of the reference's linear-solver factory (hydro2d.hpp:194-218, linear.hpp:533-782): rows in s->A (hyperplane-
+// major), constants R, result X (both hyperplane-major).  lu runs the box dataflow; the iterative solvers are the matrix
+// kernels of hg_solvers.cuh with the shared lu_relaxed_* parameters.  Scratch: t1, t2 (hyperplane-major, lu_relaxed), the
+// natural-layout staging arrays An, w1, w2, pc (Jacobi).  One GPU (the slab kernels exist for lu and the pressure sweeps only).
+static int solve_system(hg_state* s, int solver, double* R, double* X, double* t1, double* t2, int* it, double* df) {
+  const hg_config& c = s->cfg;
+  const unsigned gb = nblk(s->nc);
+  *it = 0; *df = 0.;
+  if (solver == HG_LS_LU) { double* Rs[1] = {R}; double* Xs[1] = {X}; return solve_lu(s, 1, Rs, Xs); }
+  if (s->world > 1) { s->err = "multi-GPU slabs: only lu (and gauss_seidel for the pressure) are decomposed"; return HG_ERR_INVALID; }
+  if (solver == HG_LS_GAUSS_SEIDEL) {
+    auto launch = [&](int sb, int se) -> int {
+      SorArgs a; for (int t = 0; t < 7; ++t) a.A[t] = s->A[t];
+      a.R = R; a.X = X; a.diff = s->diffs; a.s_begin = sb; a.s_end = se; a.omega = c.lu_relaxed_relaxation_factor; a.tt = s->tt;
+      if (s->dim == 3) return coop_launch(s, k_sor_matrix_persistent<3>, s->grid_solver, s->geo, a);
+      return coop_launch(s, k_sor_matrix_persistent<2>, s->grid_solver, s->geo, a);
+    };
+    return run_sor(s, X, s->nsh, c.lu_relaxed_tolerance, c.lu_relaxed_num_iters_limit, launch, it, df);
+  }
+  if (solver == HG_LS_LU_RELAXED)
+    return run_lu_relaxed(s, R, X, t1, t2, c.lu_relaxed_tolerance, c.lu_relaxed_num_iters_limit, c.lu_relaxed_relaxation_factor, it, df);
+  if (solver == HG_LS_JACOBI) {
+    for (int t = 0; t < 7; ++t) {
+      if (s->dim == 2 && (t == CZM || t == CZP)) continue;
+      DIMSEL(s, k_from_sheared, gb, 256, s->geo, s->A[t], s->An[t]);
+    }
+    DIMSEL(s, k_from_sheared, gb, 256, s->geo, R, s->w1);
+    if (int rc = run_jacobi(s, s->An, nullptr, s->w1, c.lu_relaxed_tolerance, c.lu_relaxed_num_iters_limit, c.lu_relaxed_relaxation_factor, it, df)) return rc;
+    DIMSEL(s, k_to_sheared, gb, 256, s->geo, s->pc, X);
+    return 0;
+  }
+  s->err = "Unknown linear solver";
+  return HG_ERR_INVALID;
 }
 
 // ------------------------------------------------------------------ properties / statistics
@@ -911,6 +956,17 @@ extern "C" int hg_fluid_start_step(hg_handle s) {   // fluid.hpp:793-812
   return 0;
 }
 
+// the dim component systems share their matrix (conv_diff.hpp:149-259): lu solves them in one pass, the iterative solvers
+// of the factory one after the other (pressure arrays PP / RP are free at this point: scratch of lu_relaxed)
+static int solve_momentum(hg_state* s) {
+  if (s->cfg.linear_solver_velocity == HG_LS_LU) return solve_lu(s, s->dim);
+  for (int n = 0; n < s->dim; ++n) {
+    int it; double df;
+    if (int rc = solve_system(s, s->cfg.linear_solver_velocity, s->R[n], s->X[n], s->PP, s->RP, &it, &df)) return rc;
+  }
+  return 0;
+}
+
 extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
   if (!s) return HG_ERR_INVALID;
   cudaSetDevice(s->dev);
@@ -967,7 +1023,7 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
       bdf_coeffs(s->dt, c.time_second_order, a.co);
       a.relax = c.velocity_relaxation_factor; a.coeffsum = s->dc;
       k_fb_momentum<<<fg, FT_THREADS, 0, s->st>>>(s->geo, s->slow, a); ++s->launches; }
-    if (int rc = solve_lu(s, 3)) return rc;
+    if (int rc = solve_momentum(s)) return rc;
     k_ft_apply_corr<3><<<fg, FT_THREADS, 0, s->st>>>(s->geo, cp3(s->u[L_IP]), cp3(s->X), p3(s->u[L_IC])); ++s->launches;
     tpop(s);
   } else {
@@ -1004,7 +1060,7 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
       k_assemble<2, K_VEL, 2><<<gb, 256, 0, s->st>>>(s->geo, a);
       ++s->launches;
     }
-    if (int rc = solve_lu(s, s->dim)) return rc;
+    if (int rc = solve_momentum(s)) return rc;
     if (s->dim == 3) { k_apply_corr<3, 3><<<gb, 256, 0, s->st>>>(s->geo, cp3(s->u[L_IP]), cp3(s->X), p3(s->u[L_IC])); }
     else { k_apply_corr<2, 2><<<gb, 256, 0, s->st>>>(s->geo, cp3(s->u[L_IP]), cp3(s->X), p3(s->u[L_IC])); }
     ++s->launches; }
@@ -1201,7 +1257,8 @@ extern "C" int hg_heat_step(hg_handle s) {   // heat.hpp:69-84 + conv_diff.hpp:1
   if (s->dim == 3) { k_assemble<3, K_TEMP, 1><<<gb, 256, 0, s->st>>>(s->geo, a); }
   else { k_assemble<2, K_TEMP, 1><<<gb, 256, 0, s->st>>>(s->geo, a); }
   ++s->launches;
-  if (int rc = solve_lu(s, 1)) return rc;
+  { int it; double df;
+    if (int rc = solve_system(s, c.linear_solver_heat, s->R[0], s->X[0], s->PP, s->RP, &it, &df)) return rc; }
   CP3 prev, X; P3 curr;
   for (int d = 0; d < 3; ++d) { prev.p[d] = s->T[L_TC]; X.p[d] = s->X[d]; curr.p[d] = s->T[L_IC]; }
   if (s->dim == 3) { k_apply_corr<3, 1><<<gb, 256, 0, s->st>>>(s->geo, prev, X, curr); }
@@ -1392,14 +1449,13 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     if (cfg->condition_kind[sd] == HG_BC_OUTLET) return fail_create(nullptr, HG_ERR_INVALID, "outlet conditions are not on the GPU path");
   for (int id : {cfg->linear_solver_velocity, cfg->linear_solver_pressure, cfg->linear_solver_heat})
     if (id < HG_LS_LU || id > HG_LS_JACOBI) return fail_create(nullptr, HG_ERR_INVALID, "Unknown linear solver");
-  if (cfg->linear_solver_velocity != HG_LS_LU) return fail_create(nullptr, HG_ERR_INVALID, "linear_solver_velocity: only lu runs on the GPU path");
-  if (cfg->heat_enable && cfg->linear_solver_heat != HG_LS_LU) return fail_create(nullptr, HG_ERR_INVALID, "linear_solver_heat: only lu runs on the GPU path");
-  if (cfg->linear_solver_pressure == HG_LS_LU) return fail_create(nullptr, HG_ERR_INVALID, "linear_solver_pressure: lu is not iterated for the pressure system on the GPU path");
+  if (cfg->world_size > 1 && (cfg->linear_solver_velocity != HG_LS_LU || (cfg->heat_enable && cfg->linear_solver_heat != HG_LS_LU)))
+    return fail_create(nullptr, HG_ERR_INVALID, "multi-GPU slabs support lu for the momentum and temperature systems");
   if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size || cfg->world_size > 64)
     return fail_create(nullptr, HG_ERR_INVALID, "bad world_size / rank");
   if (cfg->world_size > 1 && (cfg->dim != 3 || cfg->Nz < 2 * cfg->world_size))
     return fail_create(nullptr, HG_ERR_INVALID, "z-slab decomposition needs dim 3 and at least 2 planes per rank");
-  if (cfg->world_size > 1 && (cfg->linear_solver_pressure == HG_LS_LU_RELAXED || cfg->linear_solver_pressure == HG_LS_JACOBI))
+  if (cfg->world_size > 1 && cfg->linear_solver_pressure != HG_LS_GAUSS_SEIDEL)
     return fail_create(nullptr, HG_ERR_INVALID, "multi-GPU slabs support gauss_seidel for the pressure system");
   if (cfg->world_size > SLAB_MAX_WORLD) return fail_create(nullptr, HG_ERR_INVALID, "world_size too large");
   int ndev = 0;
@@ -1470,7 +1526,7 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     for (int d = 0; d < dim; ++d) { T.force[d] = cells(); T.stforce[d] = cells(); T.gp[d] = cells(); T.fcr[d] = cells(); T.fs[d] = cells(); }
     for (int q = 0; q < dim * dim; ++q) T.G[q] = cells();
     for (int q = 0; q < 7; ++q) T.A[q] = take(s->nsh);
-    if (dim == 3) for (int q = 0; q < 10; ++q) T.An[q] = cells();
+    for (int q = 0; q < (dim == 3 ? 10 : 7); ++q) T.An[q] = cells();   // (2-D: natural-layout rows of the Jacobi solver)
     for (int n = 0; n < dim; ++n) { T.R[n] = take(s->nsh); T.X[n] = take(s->nsh); }
     // the tile sweeps read a few hyperplanes beyond both ends of the solution and of the x+/y+ coefficient arrays:
     // GT_PAD zero hyperplanes around them (never written)

@@ -48,7 +48,10 @@ def main():
     cavity_sample()
     if not refrun.available():
         raise SystemExit("oracle/_ref/ref_dump missing: run `make -C oracle ref` first")
+    only = os.environ.get("GOLDEN_ONLY")   # comma-separated case names: (re)generate just these
     for name, (p, nsteps) in REF_CASES.items():
+        if only and name not in only.split(","):
+            continue
         res, _ = refrun.run_ref_dump(p, nsteps, iters=True)
         # the reference's own step() must give the same fields as the --iters call sequence
         res2, _ = refrun.run_ref_dump(p, nsteps, iters=False)

@@ -90,6 +90,13 @@ GOLDEN_CASES = {
     "dam2d_36x20": (broken_dam_2d(36, 20, lu_relaxed_num_iters_limit=50), 3),
     "dam3d_32x10x10": (broken_dam_3d(32, 10, 10, lu_relaxed_num_iters_limit=40), 2),
     "thermal2d_32x16": (thermal_2d(), 3),
+    # the linear-solver factory (hydro2d.hpp:194-218) applies to every system: velocity, pressure, temperature
+    "cavity_12_velgs_plu": (cavity(12, num_iterations_limit=4, linear_solver_velocity="gauss_seidel", linear_solver_pressure="lu",
+                                   lu_relaxed_num_iters_limit=25, lu_relaxed_tolerance=1e-9), 3),
+    "rt3d_8_veljacobi": (rt3d(8, linear_solver_velocity="jacobi", lu_relaxed_num_iters_limit=40, lu_relaxed_tolerance=1e-7,
+                              lu_relaxed_relaxation_factor=0.9), 2),
+    "thermal2d_24x12_vellur_heatgs": (thermal_2d(24, 12, linear_solver_velocity="lu_relaxed", linear_solver_heat="gauss_seidel",
+                                                 lu_relaxed_num_iters_limit=12, lu_relaxed_relaxation_factor=0.7), 2),
 }
 
 
