@@ -9,6 +9,8 @@
 // reference's headers (never copied) and linked with the reference's objects and libhydro_gpu.so
 // (hydro_b200/host/Makefile); it is the only reference-facing file a maintainer has to add.
 #include <cstring>
+#include <fstream>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -22,6 +24,15 @@ template <int DIM>
 class hydro_gpu : public TModule {
   hg::Handle h_;
   hg_step_stats st_{};
+  // output (hydro<Mesh>::InitOutput / write_results, hydro2d.hpp:689-927, 1623-1652): the reference's ParaView session
+  // (output_paraview.hpp:34-173) and plain scalar session (output.hpp:230-264) restated over fields fetched from the device at
+  // frame times only; same files, same schedule, values printed by the same stream formatting
+  bool no_output_ = false;
+  std::unique_ptr<std::ofstream> pvd_, scalar_;
+  std::string filename_field_;
+  size_t timestep_ = 0;
+  double last_frame_time_ = 0., last_frame_scalar_time_ = 0.;
+  std::vector<std::string> scalar_names_;
 
   void vec(const char* name, double out[3]) {
     for (int d = 0; d < 3; ++d) out[d] = 0.;
@@ -119,14 +130,122 @@ class hydro_gpu : public TModule {
     }
   }
 
+  bool out_on(const std::string& name) { const std::string k = "output_" + name; return P_bool.exist(k) && P_bool[k]; }
+  void init_output() {
+    no_output_ = P_bool["no_output"];
+    if (no_output_) return;
+    for (const char* k : {"output_factor_x", "output_factor_y", "output_factor_z"})
+      if (P_int.exist(k) && P_int[k] != 1 && (DIM == 3 || std::string(k) != "output_factor_z"))
+        throw std::runtime_error("hydro_gpu: output_factor_* other than 1 is not on the GPU path");
+    for (const char* k : {"radiation", "volume_source", "divergence", "curvature"})
+      if (out_on(k)) throw std::runtime_error(std::string("hydro_gpu: output_") + k + " is not on the GPU path");
+    for (int i = 0; i < h_.config().num_phases; ++i)
+      for (const char* k : {"mass_source_", "mass_fraction_", "density_", "target_density_"})
+        if (out_on(k + IntToStr(i))) throw std::runtime_error(std::string("hydro_gpu: output_") + k + IntToStr(i) + " is not on the GPU path");
+    if (P_string["field_output_format"] != "paraview") throw std::runtime_error("hydro_gpu: field_output_format must be paraview");
+    // scalar content (hydro2d.hpp:824-893); the in / out flux statistics (hydro2d.hpp:1473-1507) are zero for closed walls
+    // and are not accumulated here
+    scalar_names_ = {"time", "num_iters", "iter_diff_velocity"};
+    const int np = h_.config().num_phases;
+    for (int i = 0; i < np; ++i) for (const char* k : {"mass_", "mass_in_", "mass_out_"}) scalar_names_.push_back(k + IntToStr(i));
+    for (int i = 0; i < np; ++i) for (const char* k : {"volume_", "volume_in_", "volume_out_"}) scalar_names_.push_back(k + IntToStr(i));
+    for (int i = 0; i < np; ++i) for (const char* k : {"pd_min_", "pd_max_"}) scalar_names_.push_back(k + IntToStr(i));
+    for (int i = 0; i < np; ++i) {
+      scalar_names_.push_back("cx_" + IntToStr(i)); scalar_names_.push_back("cy_" + IntToStr(i));
+      if (DIM > 2) scalar_names_.push_back("cz_" + IntToStr(i));
+      scalar_names_.push_back("vx_" + IntToStr(i)); scalar_names_.push_back("vy_" + IntToStr(i));
+      if (DIM > 2) scalar_names_.push_back("vz_" + IntToStr(i));
+    }
+    if (!P_string.exist(_plt_title)) P_string.set(_plt_title, P_string[_exp_name]);
+    if (!P_string.exist("filename_field")) P_string.set("filename_field", P_string[_exp_name] + ".field");
+    if (!P_string.exist("filename_scalar")) P_string.set("filename_scalar", P_string[_exp_name] + ".scalar");
+    filename_field_ = P_string["filename_field"];
+    pvd_.reset(new std::ofstream(filename_field_ + ".pvd"));
+    *pvd_ << "<?xml version=\"1.0\"?>\n<VTKFile type=\"Collection\" version=\"0.1\" byte_order=\"LittleEndian\">\n  <Collection>\n";
+    scalar_.reset(new std::ofstream(P_string["filename_scalar"] + ".dat"));
+    for (auto& n : scalar_names_) *scalar_ << n << " ";
+    *scalar_ << std::endl;
+    for (int i = 0; i < np; ++i)
+      for (const char* k : {"stat_mass_in_", "stat_mass_out_", "stat_volume_in_", "stat_volume_out_"})
+        if (!P_double.exist(k + IntToStr(i))) P_double.set(k + IntToStr(i), 0.);
+  }
+  void write_scalar() {   // SessionPlainScalar::Write
+    double rs = 1.;
+    h_.Check(hg_fluid_convergence_indicator(h_.get(), &rs));
+    for (auto& n : scalar_names_) {
+      if (n == "time") *scalar_ << P_double["t"] << " ";
+      else if (n == "num_iters") *scalar_ << static_cast<double>(P_int["s"]) << " ";
+      else if (n == "iter_diff_velocity") *scalar_ << rs << " ";
+      else *scalar_ << P_double["stat_" + n] << " ";
+    }
+    *scalar_ << std::endl;
+  }
+  void data_array(std::ostream& out, const std::string& name, int ncomp) {
+    out << "        <DataArray Name=\"" << name << "\" NumberOfComponents=\"" << ncomp << "\" type=\"Float32\" format=\"ascii\">\n";
+  }
+  void write_frame(double time) {   // SessionParaviewStructured::Write
+    const std::string datafile = filename_field_ + "." + IntToStr(static_cast<int>(timestep_)) + ".vts";
+    *pvd_ << "    <DataSet timestep=\"" << time << "\" group=\"\" part=\"0\" file=\"" << datafile << "\"/>\n";
+    pvd_->flush();
+    ++timestep_;
+    const hg_config& c = h_.config();
+    const int n[3] = {c.Nx, c.Ny, DIM == 3 ? c.Nz : 0};
+    std::ofstream out(datafile);
+    out << "<?xml version=\"1.0\"?>\n<VTKFile type=\"StructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n";
+    for (const char* tag : {"  <StructuredGrid WholeExtent=\"", "    <Piece Extent=\""})
+      out << tag << "0 " << n[0] << " 0 " << n[1] << " 0 " << n[2] << "\">\n";
+    // node coordinates: InitUniformMesh (mesh.hpp:722-736), lb + (midx / mesh_size) * (rt - lb), x fastest
+    auto node = [&](int d, int i) { return d < DIM ? c.A[d] + (static_cast<double>(i) / n[d]) * (c.B[d] - c.A[d]) : 0.; };
+    const int nn[3] = {n[0] + 1, n[1] + 1, DIM == 3 ? n[2] + 1 : 1};
+    out << "      <PointData>\n";
+    for (int d = 0; d < 3; ++d) {
+      const std::string nm(1, "xyz"[d]);
+      if (!out_on(nm)) continue;
+      data_array(out, nm, 1);
+      for (int k = 0; k < nn[2]; ++k) for (int j = 0; j < nn[1]; ++j) for (int i = 0; i < nn[0]; ++i) {
+        const int idx[3] = {i, j, k};
+        out << node(d, idx[d]) << " ";
+      }
+      out << "\n        </DataArray>\n";
+    }
+    out << "      </PointData>\n      <CellData>\n";
+    std::vector<double> buf;
+    auto cell = [&](const std::string& nm, int field) {
+      if (!out_on(nm)) return;
+      data_array(out, nm, 1);
+      if (field < 0) buf.assign(h_.NumCells(), 0.); else h_.Get(field, buf);
+      for (double v : buf) out << v << " ";
+      out << "\n        </DataArray>\n";
+    };
+    // content pool order (hydro2d.hpp:711-818)
+    cell("velocity_x", HG_F_VELOCITY_X); cell("velocity_y", HG_F_VELOCITY_Y); cell("velocity_z", DIM == 3 ? HG_F_VELOCITY_Z : -1);
+    cell("pressure", HG_F_PRESSURE); cell("density", HG_F_DENSITY); cell("viscosity", HG_F_VISCOSITY);
+    if (c.heat_enable) cell("temperature", HG_F_TEMPERATURE); else cell("temperature", -1);
+    cell("excluded", HG_F_EXCLUDED);
+    for (int i = 0; i < c.num_phases; ++i) cell("partial_density_" + IntToStr(i), HG_F_PARTIAL_DENSITY_0 + i);
+    for (int i = 0; i < c.num_phases; ++i) cell("volume_fraction_" + IntToStr(i), HG_F_VOLUME_FRACTION_0 + i);
+    out << "      </CellData>\n      <Points>\n";
+    data_array(out, "mesh", 3);
+    for (int k = 0; k < nn[2]; ++k) for (int j = 0; j < nn[1]; ++j) for (int i = 0; i < nn[0]; ++i)
+      out << node(0, i) << " " << node(1, j) << " " << node(2, k) << " ";
+    out << "        </DataArray>\n      </Points>\n    </Piece>\n  </StructuredGrid>\n</VTKFile>\n";
+  }
+
  public:
+  ~hydro_gpu() { if (pvd_) *pvd_ << "  </Collection>\n</VTKFile>\n"; }
   explicit hydro_gpu(TExperiment* _ex) : TExperiment_ref(_ex), TModule(_ex) {
     P_int.set("last_s", 0); P_double.set("last_R", 0); P_double.set("last_Rn", 0);
     P_int.set("s_sum", 0); P_int.set("s_max", 0); P_int.set("s", 0);
+    P_int.set("current_frame", 0); P_int.set("current_frame_scalar", 0);   // hydro2d.hpp:952-953
     h_.Create(config());                       // throws std::string on failure, like the reference
     P_int.set("cells_number", static_cast<int>(h_.NumCells()));
     h_.Check(hg_get_stats(h_.get(), &st_));   // the CalcStat of the constructor (hydro2d.hpp:962) ran inside hg_create
     publish_stat();
+    init_output();
+    if (!no_output_) {   // hydro2d.hpp:966-971
+      if (P_int["max_frame_index"] > 0) write_frame(0.);
+      write_scalar();
+    }
   }
   void step() override {
     ex->timer_.Push("step");
@@ -142,10 +261,24 @@ class hydro_gpu : public TModule {
     }
     publish_stat();
   }
-  void write_results(bool force = false) override {
-    // mesh frames (.vts) are the next scope row; the scalar series is logged
-    if (force && !ecast(P_bool("no_output")))
-      logger() << "gpu final: t=" << st_.time << " volume_0=" << st_.volume[0] << " pressure sweeps=" << st_.pressure_sweeps_total;
+  void write_results(bool force = false) override {   // hydro<Mesh>::write_results, hydro2d.hpp:1623-1652
+    if (no_output_) return;
+    const double time = st_.time;
+    const double total_time = P_double["T"];
+    const size_t max_frame_index = P_int["max_frame_index"];
+    const double frame_duration = total_time / max_frame_index;
+    if (force || (!ecast(P_bool("no_mesh_output")) && time >= last_frame_time_ + frame_duration)) {
+      last_frame_time_ += frame_duration;
+      write_frame(time);
+      logger() << "Frame " << (P_int["current_frame"]++) << ": t=" << time;
+    }
+    const size_t max_frame_scalar_index = P_int["max_frame_scalar_index"];
+    const double frame_scalar_duration = total_time / max_frame_scalar_index;
+    if (force || time >= last_frame_scalar_time_ + frame_scalar_duration) {
+      last_frame_scalar_time_ = time;
+      write_scalar();
+      logger() << "Frame_scalar " << (P_int["current_frame_scalar"]++) << ": t=" << time;
+    }
   }
 };
 

@@ -83,3 +83,34 @@ def test_solver_shim_protocol_equals_hg_step(case):
         assert np.array_equal(a, b), n
     m = re.search(r"indicator (\S+)", r.stdout)
     assert float(m.group(1)) == st.convergence_indicator
+
+
+@pytest.mark.gpu
+def test_module_writes_the_reference_output_files():
+    """SURVEY 8f rank 2 inside the plugin: hydro_gpu<DIM>::write_results writes the ParaView frames, the .pvd collection and the
+    scalar series on the reference's schedule (hydro2d.hpp:1623-1652, output_paraview.hpp:34-173, output.hpp:230-264).  The cavity
+    case starts from identical fields on both paths (no transcendental initial condition), the GPU path is bit-exact on it, so
+    every file must equal the CPU module's byte for byte."""
+    import refrun
+    assert os.access(BIN, os.X_OK), "hydro_b200/host/_build/hydro_gpu not built"
+    files = {}
+    for m in ("hydro2d", "hydro2d_gpu"):
+        p = cases.cavity(24, num_iterations_limit=6, lu_relaxed_num_iters_limit=40)
+        p["MODULE"] = m
+        nsteps = 6
+        p["T"] = float(p["dt"]) * (nsteps - 0.5)
+        p["max_frame_index"] = 3
+        p["max_frame_scalar_index"] = 6
+        p["output_viscosity"] = 1
+        with tempfile.TemporaryDirectory() as tmp:
+            refrun.write_script(p, os.path.join(tmp, "start.hydroconf"), start=True)
+            r = subprocess.run([BIN, "start.hydroconf"], cwd=tmp, capture_output=True, text=True, timeout=600,
+                               env=dict(os.environ, OMP_NUM_THREADS="4"))
+            log = open(os.path.join(tmp, "exp.log")).read() if os.path.exists(os.path.join(tmp, "exp.log")) else ""
+            assert "Experiment terminated" in log, (r.stdout[-800:], r.stderr[-800:], log[-800:])
+            files[m] = {f: open(os.path.join(tmp, f), "rb").read() for f in sorted(os.listdir(tmp))
+                        if f.endswith((".vts", ".pvd", ".dat"))}
+    a, b = files["hydro2d"], files["hydro2d_gpu"]
+    assert sorted(a) == sorted(b) and len([f for f in a if f.endswith(".vts")]) >= 3, (sorted(a), sorted(b))
+    for f in a:
+        assert a[f] == b[f], f
