@@ -696,6 +696,42 @@ __global__ void __launch_bounds__(256, 8) k_advect(Geo g, const double* __restri
   out[c] = u[c] + -dt / g.vol * fsum;
 }
 
+// Interface sharpening (advection.hpp:479-529), once per field after the advection stages: gc = Gradient(Interpolate(u)) is in
+// gcv (k_grad_pd); a face carries ff = |F nf| nf (sharp A |gf| - af (1 - af / am)) with gf = Interpolate(gc, zero derivative),
+// n = gf / (|gf| + 1e-6), nf = n . normal, where |gf| >= 1; a cell gets u + dt 0 (sources) + dt sum(outward ff) / V
+template <int DIM>
+DV double sharp_face(const Geo& g, const double* __restrict__ u, const double* __restrict__ pdinit, CP3 gcv,
+                     const double* __restrict__ F, double sharp, double am, int d, int fi, int fj, int fk) {
+  double n[3] = {0., 0., 0.}, sq = 0.;
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) { n[c] = face_value<DIM, K_NEUMANN0>(g, gcv.p[c], d, fi, fj, fk, 0); sq += n[c] * n[c]; }
+  const double nrm = sqrt(sq);
+  if (nrm < 1.) return 0.;
+  double nf = 0.;
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) { n[c] /= (nrm + 1e-6); nf += n[c] * (c == d ? 1. : 0.); }
+  const double af = face_value<DIM, K_PD>(g, u, d, fi, fj, fk, 0, pdinit);
+  const double uf = F[fidx(g, d, fi, fj, fk)];
+  const double epsh = sharp * g.area[d];
+  return fabs(uf * nf) * nf * (epsh * nrm - af * (1. - af / am));
+}
+template <int DIM>
+__global__ void __launch_bounds__(256, 4) k_sharpen(Geo g, const double* __restrict__ u, const double* __restrict__ pdinit, CP3 gcv,
+                                                   const double* __restrict__ F, double dt, double sharp, double am, double* __restrict__ out) {
+  CELL_LOOP_PROLOG(g)
+  double sh = 0.;
+#pragma unroll
+  for (int q = 0; q < 2 * DIM; ++q) {
+    const int d = q >> 1, o = q & 1;
+    const int fi = i + (d == 0 ? o : 0), fj = j + (d == 1 ? o : 0), fk = k + (d == 2 ? o : 0);
+    sh += (o ? 1. : -1.) * sharp_face<DIM>(g, u, pdinit, gcv, F, sharp, am, d, fi, fj, fk);
+  }
+  double v = u[c];
+  v += dt * 0.;
+  v += dt * sh / g.vol;
+  out[c] = v;
+}
+
 // ---------------------------------------------------------------- statistics (CalcStat, hydro2d.hpp:1432-1466)
 // out[ph*12 + {0 volume, 1..3 centre sums, 4..6 velocity sums}] (atomicAdd), out[ph*12+7] pd_min, +8 pd_max
 struct StatArgs { int np; const double* vf[3]; const double* pd[3]; const double* u[3]; double* out; };

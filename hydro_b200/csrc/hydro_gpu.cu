@@ -1225,6 +1225,15 @@ extern "C" int hg_advection_step(hg_handle s) {   // advection.hpp:417-545
       } else DIMSEL(s, k_advect, nblk(s->nc), 256, s->geo, in, s->pd_init[ph], s->F[L_TC], s->dt_adv, num_stages, stage, out);
       in = out;
     }
+    if (std::fabs(c.sharp) > 1e-10) {   // interface sharpening, once per field after the stages (advection.hpp:479-529)
+      double* const sharpened = bufs[num_stages % 2];   // (the input of the last stage, no longer needed, or the other buffer)
+      XCH(s, 2, out);
+      P3 gc; CP3 gcc; for (int d = 0; d < 3; ++d) { gc.p[d] = s->G[d]; gcc.p[d] = s->G[d]; }
+      DIMSEL(s, k_grad_pd, nblk(s->nc), 256, s->geo, out, s->pd_init[ph], gc);
+      XCH(s, 1, s->G[0], s->G[1], s->dim > 2 ? s->G[2] : nullptr);
+      DIMSEL(s, k_sharpen, nblk(s->nc), 256, s->geo, out, s->pd_init[ph], gcc, s->F[L_TC], s->dt_adv, c.sharp, c.density[ph], sharpened);
+      out = sharpened;
+    }
     // FinishStep: time_curr = iter_curr
     if (out == s->pd[ph][L_IC]) std::swap(s->pd[ph][L_TC], s->pd[ph][L_IC]);
     else std::swap(s->pd[ph][L_TC], s->pd[ph][L_IP]);
@@ -1444,7 +1453,6 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
   if (cfg->num_phases < 1 || cfg->num_phases > HG_MAX_PHASES) return fail_create(nullptr, HG_ERR_INVALID, "num_phases must be 1..3");
   if (cfg->simpler) return fail_create(nullptr, HG_ERR_INVALID, "simpler 1 is not on the GPU path");
   if (cfg->force_geometric_average) return fail_create(nullptr, HG_ERR_INVALID, "force_geometric_average 1 is not on the GPU path");
-  if (cfg->sharp != 0.) return fail_create(nullptr, HG_ERR_INVALID, "sharp != 0 is not on the GPU path");
   for (int sd = 0; sd < 2 * cfg->dim; ++sd)
     if (cfg->condition_kind[sd] == HG_BC_OUTLET) return fail_create(nullptr, HG_ERR_INVALID, "outlet conditions are not on the GPU path");
   for (int id : {cfg->linear_solver_velocity, cfg->linear_solver_pressure, cfg->linear_solver_heat})

@@ -15,8 +15,7 @@
  *
  * Not restated (the product rejects the same options): outlet conditions
  * (fluid.hpp:542-600), SIMPLER (fluid.hpp:1060-1155), geometric force averaging,
- * phase slip/settling, chemistry/radiation, compressibility, interface
- * sharpening (`sharp`), PIC advection.
+ * phase slip/settling, chemistry/radiation, compressibility, PIC advection.
  */
 #include "hydro_oracle.h"
 
@@ -701,7 +700,39 @@ static void advection_iteration(struct ho_state* s) {                /* advectio
         curr[c] += -s->dt_adv / s->vol * fsum;
       }
     }
-    /* sharpening disabled (sharp == 0): adds dt*0/V; sources are zero (chem_intensity 0) */
+    /* Interface sharpening, advection.hpp:479-529 (once per field, after the stages).  With sharp == 0 every ff is 0 and the
+     * update adds dt*0/V (the sources are zero: chem_intensity 0): skipped, it cannot change a value */
+    if (fabs(s->cfg.sharp) > 1e-10) {
+      double* af = s->wf; double* ff = s->kf;
+      double* gc[3] = {s->w2[0], s->w2[1], s->w2[2]};
+      interp(s, curr, K_PD, ph, af);                               /* :488 */
+      gradient(s, af, gc);                                         /* :489 */
+      for (int d = 0; d < dim; ++d) interp(s, gc[d], K_NEUMANN0, 0, s->ffe[d]);   /* :490, zero-derivative for Vect */
+      memset(ff, 0, s->nf * sizeof(double));
+      const double am = s->cfg.density[ph];                        /* sharp_max_ = v_true_density, hydro2d.hpp:600 */
+      for (int d = 0; d < dim; ++d) {
+        int ex = s->n[0] + (d == 0), ey = s->n[1] + (d == 1), ez = s->n[2] + (d == 2);
+        for (int k = 0; k < ez; ++k) for (int j = 0; j < ey; ++j) for (int i = 0; i < ex; ++i) {
+          size_t f = fidx(s, d, i, j, k);
+          double n[3] = {0., 0., 0.}, sq = 0.;
+          for (int c = 0; c < dim; ++c) { n[c] = s->ffe[c][f]; sq += n[c] * n[c]; }
+          const double nrm = sqrt(sq);
+          if (nrm < 1.) continue;                                  /* th = 1 */
+          double nf = 0.;
+          for (int c = 0; c < dim; ++c) { n[c] /= (nrm + 1e-6); nf += n[c] * (c == d ? 1. : 0.); }   /* n.dot(GetNormal) */
+          const double uf = F[f];
+          const double epsh = s->cfg.sharp * s->area[d];
+          ff[f] = fabs(uf * nf) * nf * (epsh * nrm - af[f] * (1. - af[f] / am));
+        }
+      }
+      for (int k = 0; k < s->n[2]; ++k) for (int j = 0; j < s->n[1]; ++j) for (int i = 0; i < s->n[0]; ++i) {
+        size_t c = cidx(s, i, j, k);
+        curr[c] += s->dt_adv * 0.;                                 /* sources :513-515 */
+        double sh = 0.;
+        for (int q = 0; q < 2 * dim; ++q) sh += ((q & 1) ? 1. : -1.) * ff[nface(s, i, j, k, q)];
+        curr[c] += s->dt_adv * sh / s->vol;                        /* :529 */
+      }
+    }
   }
 }
 
@@ -874,7 +905,7 @@ static int inside(const double lb[3], const double rt[3], const double x[3], int
 int ho_create(const hg_config* cfg, ho_handle* out) {
   if (!cfg || !out) return HG_ERR_INVALID;
   if ((cfg->dim != 2 && cfg->dim != 3) || cfg->num_phases < 1 || cfg->num_phases > HG_MAX_PHASES ||
-      cfg->simpler || cfg->force_geometric_average || cfg->sharp != 0.) {
+      cfg->simpler || cfg->force_geometric_average) {
     snprintf(g_err, sizeof g_err, "unsupported configuration"); return HG_ERR_INVALID;
   }
   for (int sd = 0; sd < 2 * cfg->dim; ++sd) if (cfg->condition_kind[sd] == HG_BC_OUTLET) {

@@ -95,6 +95,9 @@ GOLDEN_CASES = {
                                    lu_relaxed_num_iters_limit=25, lu_relaxed_tolerance=1e-9), 3),
     "rt3d_8_veljacobi": (rt3d(8, linear_solver_velocity="jacobi", lu_relaxed_num_iters_limit=40, lu_relaxed_tolerance=1e-7,
                               lu_relaxed_relaxation_factor=0.9), 2),
+    # interface sharpening (advection.hpp:479-529), with and without the directional split
+    "rt3d_8_sharp_split": (rt3d(8, sharp=0.05, tvd_split=1), 3),
+    "dam2d_32x16_sharp": (broken_dam_2d(32, 16, sharp=0.02, lu_relaxed_num_iters_limit=40), 3),
     "thermal2d_24x12_vellur_heatgs": (thermal_2d(24, 12, linear_solver_velocity="lu_relaxed", linear_solver_heat="gauss_seidel",
                                                  lu_relaxed_num_iters_limit=12, lu_relaxed_relaxation_factor=0.7), 2),
 }

@@ -44,7 +44,7 @@ def test_slabs_equal_single_gpu(case, world, kernel, monkeypatch):
          "rt3d_20x12x17": cases.rt3d(8, Nx=20, Ny=12, Nz=17, lu_relaxed_num_iters_limit=30),
          "dam3d_32x10x12": cases.broken_dam_3d(32, 10, 12, lu_relaxed_num_iters_limit=40),
          # surface tension (CalcForce, hydro2d.hpp:1318-1370) and the temperature equation (heat.hpp:19-93) on slabs
-         "rt3d_stf_20x12x16": cases.rt3d(8, Nx=20, Ny=12, Nz=16, lu_relaxed_num_iters_limit=20, sigma=0.07, tvd_split=1),
+         "rt3d_stf_20x12x16": cases.rt3d(8, Nx=20, Ny=12, Nz=16, lu_relaxed_num_iters_limit=20, sigma=0.07, tvd_split=1, sharp=0.03),
          "thermal3d_24x12x15": cases.rt3d(8, Nx=24, Ny=12, Nz=15, lu_relaxed_num_iters_limit=15, heat_enable=1,
                                           heat_box_lb=(-1., -1., -1.), heat_box_rt=(2., 0.01, 2.), heat_box_temperature=1.,
                                           conductivity_0=0.01, conductivity_1=0.05),
