@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(256, 5) k_assemble(Geo g, AsmArgs a) {
         ddiag = have_d ? ddiag + dself : dself; have_d = true;
 #pragma unroll
         for (int n = 0; n < NCOMP; ++n) {
-          const double val = (KIND == K_VEL) ? g.bcvel[f.side][n] : g.heat_T;
+          const double val = (KIND == K_VEL) ? bc_velocity(g, f.side, n, d, fi, fj, fk) : g.heat_T;
           cconst[n] += (val * Ff) * sgn;
           dconst[n] += (((alpha * val) * (-muf)) * g.area[d]) * sgn;
         }
@@ -432,7 +432,7 @@ DV double fstar_face(const Geo& g, const FstarArgs& a, int d, int fi, int fj, in
     const double compact = (a.pprev[f.cp] - a.pprev[f.cm]) / g.h[d] * A - ffe * A;
     return (vfi + a.rc * (wide - compact) / dfc + 0) - mv;
   }
-  const double ffu = (f.type == FT_BOUND) ? g.bcvel[f.side][d] : 0.;
+  const double ffu = (f.type == FT_BOUND) ? bc_velocity(g, f.side, d, d, fi, fj, fk) : 0.;
   return ffu * A - mv;
 }
 template <int DIM>
@@ -730,6 +730,100 @@ __global__ void __launch_bounds__(256, 4) k_sharpen(Geo g, const double* __restr
   v += dt * 0.;
   v += dt * sh / g.vol;
   out[c] = v;
+}
+
+// ---------------------------------------------------------------- outlet conditions (fluid.hpp:542-600)
+// Pass A (one thread per boundary face of the domain sides): every outlet face takes the velocity of its cell; the face's
+// contributions to the outlet flux, the outlet area and the inlet flux are stored at the face's position in the reference's
+// summation order (ascending face index: direction, then k, j, i).  Pass B adds them in exactly that order (one thread adds,
+// the block stages the terms in shared memory), so the balance has the reference's bits; directions without an inlet or
+// outlet side are skipped.  Pass C applies the additive normal correction.
+struct OutletArgs { const double* u[3]; double* outvel; long long outplane; double* part; double* corr; };
+template <int DIM>
+DV bool outlet_face(const Geo& g, long long t, int& side, int& d, int& fi, int& fj, int& fk, long long& pidx) {
+  // thread -> (side, face of the side): sides 0 .. 2 DIM - 1, g.outplane slots each, of which na * nb are faces
+  side = (int)(t / g.outplane); pidx = t - (long long)side * g.outplane;
+  if (side >= 2 * DIM) return false;
+  d = side >> 1;
+  const int na = d == 0 ? g.n[1] : g.n[0], nb = d == 2 ? g.n[1] : g.n[2];   // (n[2] = 1 in 2-D)
+  if (pidx >= (long long)na * nb) return false;
+  const int a = (int)(pidx % na), b = (int)(pidx / na);
+  const int x = (side & 1) ? g.n[d] : 0;
+  fi = d == 0 ? x : a; fj = d == 1 ? x : (d == 0 ? a : b); fk = d == 2 ? x : (d == 0 || d == 1 ? b : 0);
+  return true;
+}
+// position of a domain-side face in the face-index order of its direction, and the first position of a direction
+HD long long outlet_seq(const Geo& g, int d, int hi, int fi, int fj, int fk) {
+  if (d == 0) return 2LL * (fj + (long long)g.n[1] * fk) + hi;                 // i + (nx+1) (j + ny k): i = 0, nx alternate
+  if (d == 1) return fi + (long long)g.n[0] * (hi + 2LL * fk);                 // i + nx (j + (ny+1) k): rows j = 0, ny per k
+  return fi + (long long)g.n[0] * (fj + (long long)g.n[1] * hi);               // i + nx (j + ny k): planes k = 0, nz
+}
+HD long long outlet_base(const Geo& g, int d) {
+  const long long c0 = 2LL * g.n[1] * g.n[2], c1 = 2LL * g.n[0] * g.n[2];
+  return d == 0 ? 0 : (d == 1 ? c0 : c0 + c1);
+}
+template <int DIM>
+__global__ void __launch_bounds__(256) k_outlet_collect(Geo g, OutletArgs a) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int side, d, fi, fj, fk; long long pidx;
+  if (!outlet_face<DIM>(g, t, side, d, fi, fj, fk, pidx)) return;
+  double v[3] = {0., 0., 0.};   // outlet flux, outlet area, inlet flux
+  const FaceInfo f = face_info<DIM>(g, d, fi, fj, fk);
+  if (f.type == FT_BOUND && f.side < 6) {
+    const long long cc = f.id == 0 ? f.cm : f.cp;
+    if (g.bckind[side] == 2) {
+      const double factor = f.id == 0 ? 1. : -1.;
+      double dot = 0.;
+#pragma unroll
+      for (int c = 0; c < DIM; ++c) {
+        const double uc = a.u[c][cc];
+        a.outvel[((long long)side * 3 + c) * a.outplane + pidx] = uc;
+        dot += uc * (c == d ? g.area[d] : 0.);
+      }
+      v[0] = dot * factor; v[1] = g.area[d];
+    } else if (g.bckind[side] == 1) {
+      const double factor = f.id == 0 ? -1. : 1.;
+      double dot = 0.;
+#pragma unroll
+      for (int c = 0; c < DIM; ++c) dot += g.bcvel[side][c] * (c == d ? g.area[d] : 0.);
+      v[2] = dot * factor;
+    }
+  }
+  const long long q = outlet_base(g, d) + outlet_seq(g, d, side & 1, fi, fj, fk);
+  a.part[3 * q] = v[0]; a.part[3 * q + 1] = v[1]; a.part[3 * q + 2] = v[2];
+}
+template <int DIM>
+__global__ void __launch_bounds__(256) k_outlet_correction(Geo g, const double* __restrict__ part, double* corr) {
+  __shared__ double sm[3 * 256];
+  double s[3] = {0., 0., 0.};
+  for (int d = 0; d < DIM; ++d) {
+    if (g.bckind[2 * d] == 0 && g.bckind[2 * d + 1] == 0) continue;   // walls on both sides: no term
+    const long long base = outlet_base(g, d), cnt = outlet_base(g, d + 1 < 3 ? d + 1 : 2) - base;
+    const long long n = d == 2 ? 2LL * g.n[0] * g.n[1] : cnt;
+    for (long long q0 = 0; q0 < n; q0 += 256) {
+      const int m = (int)(n - q0 < 256 ? n - q0 : 256);
+      for (int e = threadIdx.x; e < 3 * m; e += 256) sm[e] = part[3 * (base + q0) + e];
+      __syncthreads();
+      if (threadIdx.x == 0) for (int e = 0; e < m; ++e) { s[0] += sm[3 * e]; s[1] += sm[3 * e + 1]; s[2] += sm[3 * e + 2]; }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) *corr = (s[2] - s[0]) / s[1];   // (inlet - outlet) / outlet area
+}
+template <int DIM>
+__global__ void __launch_bounds__(256) k_outlet_apply(Geo g, OutletArgs a) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int side, d, fi, fj, fk; long long pidx;
+  if (!outlet_face<DIM>(g, t, side, d, fi, fj, fk, pidx) || g.bckind[side] != 2) return;
+  const FaceInfo f = face_info<DIM>(g, d, fi, fj, fk);
+  if (f.type != FT_BOUND || f.side >= 6) return;
+  const double factor = f.id == 0 ? 1. : -1.;
+  const double corr = *a.corr;
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) {
+    double* p = &a.outvel[((long long)side * 3 + c) * a.outplane + pidx];
+    *p = *p + ((c == d ? g.area[d] / g.area[d] : 0. / g.area[d]) * corr) * factor;
+  }
 }
 
 // ---------------------------------------------------------------- statistics (CalcStat, hydro2d.hpp:1432-1466)

@@ -18,6 +18,9 @@
 //
 // The arithmetic (term order z, y, x; one division per component) is that of k_lu_persistent: bit-identical.
 #pragma once
+#ifndef LT_SLEEP_NS
+#define LT_SLEEP_NS 200   // poll interval of the publisher warp
+#endif
 #include "hg_device.cuh"
 #include "hg_slab.cuh"
 
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(LT_THREADS, LT_CTAS_PER_SM) k_lu_tiled(Geo g, 
         for (;;) {
           const int v = lt_ld_acquire_cta(&s_prog);
           if (v != last) { lt_st_release(&a.progress[me], v); last = v; if (v == 0x7fffffff) break; }
-          else __nanosleep(200);
+          else { if (LT_SLEEP_NS > 0) __nanosleep(LT_SLEEP_NS); }
         }
       }
       __syncwarp();

@@ -71,6 +71,7 @@ struct hg_state {
   // [0]: radius-1 stencils (SIMPLE iteration), [1]: radius 2 (advection)
   bool fast = false; unsigned char* slow = nullptr; int* slow_list = nullptr; int nslow = 0;
   unsigned char* slow2 = nullptr; int* slow2_list = nullptr; int nslow2 = 0;
+  double* outvel = nullptr; double* outpart = nullptr; bool any_outlet = false; int out_blocks = 0; long long out_terms = 0;   // outlet conditions
   double* resid = nullptr;    // per-iteration convergence indicators of the current step (device, 4096)
   double* scal = nullptr;     // device scalars: [0] resid, [1] auto dt, [2..] stat (36), then diffs
   int* flag = nullptr;        // [0] scratch NaN flag (immediate checks), [1] any-excluded flag, [4..11] deferred NaN flags of a step
@@ -979,6 +980,13 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
   // from here on: *_IP hold the state the iteration starts from
 
   XCH(s, 1, s->u[L_IP][0], s->u[L_IP][1], s->u[L_IP][2], s->p[L_IP]);
+  if (s->any_outlet) {   // UpdateOutletBaseConditions + UpdateDerivedConditions (fluid.hpp:820-821)
+    OutletArgs a; for (int d = 0; d < 3; ++d) a.u[d] = s->u[L_IP][d] ? s->u[L_IP][d] : s->zero;
+    a.outvel = s->outvel; a.outplane = s->geo.outplane; a.part = s->outpart; a.corr = s->outpart + 3 * s->out_terms;
+    DIMSEL(s, k_outlet_collect, s->out_blocks, 256, s->geo, a);
+    DIMSEL(s, k_outlet_correction, 1, 256, s->geo, s->outpart, a.corr);
+    DIMSEL(s, k_outlet_apply, s->out_blocks, 256, s->geo, a);
+  }
   const bool fast = s->fast;
   const Geo gl = list_geo(s);
   const unsigned gbl = nblk(s->nslow);
@@ -1454,7 +1462,7 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
   if (cfg->simpler) return fail_create(nullptr, HG_ERR_INVALID, "simpler 1 is not on the GPU path");
   if (cfg->force_geometric_average) return fail_create(nullptr, HG_ERR_INVALID, "force_geometric_average 1 is not on the GPU path");
   for (int sd = 0; sd < 2 * cfg->dim; ++sd)
-    if (cfg->condition_kind[sd] == HG_BC_OUTLET) return fail_create(nullptr, HG_ERR_INVALID, "outlet conditions are not on the GPU path");
+    if (cfg->condition_kind[sd] == HG_BC_OUTLET && cfg->world_size > 1) return fail_create(nullptr, HG_ERR_INVALID, "multi-GPU slabs: outlet conditions are not decomposed");
   for (int id : {cfg->linear_solver_velocity, cfg->linear_solver_pressure, cfg->linear_solver_heat})
     if (id < HG_LS_LU || id > HG_LS_JACOBI) return fail_create(nullptr, HG_ERR_INVALID, "Unknown linear solver");
   if (cfg->world_size > 1 && (cfg->linear_solver_velocity != HG_LS_LU || (cfg->heat_enable && cfg->linear_solver_heat != HG_LS_LU)))
@@ -1566,6 +1574,16 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     if (!okA) return fail_create(s, HG_ERR_CUDA, "allocation failed: " + s->err);
   }
   bool ok = true;
+  for (int sd = 0; sd < 2 * dim; ++sd) if (cfg->condition_kind[sd] == HG_BC_OUTLET) s->any_outlet = true;
+  if (s->any_outlet) {   // velocities of the outlet faces: [side][component][face of the side], zero at construction (OutletAuto)
+    const long long pl = std::max({(long long)s->n[1] * s->n[2], (long long)s->n[0] * s->n[2], dim > 2 ? (long long)s->n[0] * s->n[1] : 0LL});
+    g.outplane = pl;
+    s->out_blocks = (int)nblk(2LL * dim * pl);
+    const long long nterms = 2LL * s->n[1] * s->n[2] + 2LL * s->n[0] * s->n[2] + (dim > 2 ? 2LL * s->n[0] * s->n[1] : 0LL);
+    s->out_terms = nterms;
+    ok = dalloc(s, &s->outvel, 18 * pl) == 0 && dalloc(s, &s->outpart, 3 * nterms + 8) == 0;
+    g.outvel = s->outvel;
+  }
   if (ok) { int* fp = nullptr; ok = dalloc(s, &fp, 16) == 0; s->flag = fp; }
   if (ok) { unsigned char* ep = nullptr; ok = dalloc(s, &ep, s->nxy * (s->n[2] + 2 * HG_HALO)) == 0; s->excl = ep ? ep + HG_HALO * s->nxy : nullptr; }
   if (!ok || cudaMallocHost((void**)&s->hscal, 64 * 128 * sizeof(double)) != cudaSuccess ||

@@ -13,8 +13,7 @@
  * tables computed from node coordinates (mesh3d.hpp:264-460); the two agree to
  * rounding, and exactly when N is a power of two on a unit box.
  *
- * Not restated (the product rejects the same options): outlet conditions
- * (fluid.hpp:542-600), SIMPLER (fluid.hpp:1060-1155), geometric force averaging,
+ * Not restated (the product rejects the same options): SIMPLER (fluid.hpp:1060-1155), geometric force averaging,
  * phase slip/settling, chemistry/radiation, compressibility, PIC advection.
  */
 #include "hydro_oracle.h"
@@ -39,6 +38,8 @@ struct ho_state {
   signed char* fside;     /* boundary faces: index into bcvel (0..5 sides, 6 box) */
   unsigned char* ftdir;   /* temperature: 1 = Dirichlet (heat box) */
   double bcvel[7][3];
+  double* outvel[3];      /* velocity of the outlet faces (OutletAuto, fluid.hpp:318-336), face-field sized, zero at construction */
+  int any_outlet;
   int bckind[7];
   long pfix_cell;
   double *u[4][3], *p[4], *F[4];
@@ -106,6 +107,13 @@ static double* dalloc(size_t n) {
 }
 
 /* ------------------------------------------------ Interpolate cell -> face */
+/* Dirichlet velocity of a boundary face: wall / inlet value of its side, or the outlet face's own velocity */
+static double bc_velocity(const struct ho_state* s, size_t f, int comp) {
+  const int side = (int)s->fside[f];
+  if (side < 6 && s->bckind[side] == HG_BC_OUTLET) return s->outvel[comp][f];
+  return s->bcvel[side][comp];
+}
+
 /* solver.hpp:392-470.  kind selects the MapFace of conditions:
  *   K_NONE      empty map (boundary faces stay 0)           fluid.hpp:886
  *   K_NEUMANN0  ConditionFaceDerivativeFixed(0)             fluid.hpp:723-730
@@ -137,7 +145,7 @@ static void interp(const struct ho_state* s, const double* u, int kind, int comp
       long cc = id == 0 ? cm : cp;
       int dirichlet = 0; double val = 0.;
       int k2 = kind;
-      if (kind == K_VEL) { dirichlet = 1; val = s->bcvel[(int)s->fside[f]][comp]; }
+      if (kind == K_VEL) { dirichlet = 1; val = bc_velocity(s, f, comp); }
       else if (kind == K_TEMP) { if (s->ftdir[f]) { dirichlet = 1; val = s->cfg.heat_box_temperature; } else k2 = K_NEUMANN0; }
       else if (kind == K_PD) { if (s->bckind[(int)s->fside[f]] == HG_BC_INLET) { dirichlet = 1; val = s->pd_inlet[comp][f]; } else k2 = K_NEUMANN0; }
       if (dirichlet) { res[f] = val; continue; }
@@ -381,7 +389,7 @@ static void convdiff_iteration(struct ho_state* s, double* fl[4], int kind, int 
         int id = (q & 1) ? 0 : 1;
         double factor = (id == 0 ? 1. : -1.);
         int dirichlet = 0; double val = 0.;
-        if (kind == K_VEL) { dirichlet = 1; val = s->bcvel[(int)s->fside[f]][comp]; }
+        if (kind == K_VEL) { dirichlet = 1; val = bc_velocity(s, f, comp); }
         else if (kind == K_TEMP && s->ftdir[f]) { dirichlet = 1; val = s->cfg.heat_box_temperature; }
         if (dirichlet) {
           cconst += (val * Ff) * sgn;
@@ -449,6 +457,46 @@ int ho_fluid_start_step(ho_handle s) {                               /* fluid.hp
   return 0;
 }
 
+/* UpdateOutletBaseConditions, fluid.hpp:542-600: every outlet face takes the velocity of its cell (iter_curr); a uniform
+ * normal velocity is added so that the outlet flux equals the inlet flux (boundary faces in ascending face index) */
+static void update_outlet(struct ho_state* s) {
+  if (!s->any_outlet) return;
+  const int dim = s->dim;
+  double inlet = 0., outlet = 0., area = 0.;
+  for (int pass = 0; pass < 2; ++pass) {
+    const double corr = pass ? (inlet - outlet) / area : 0.;
+    for (int d = 0; d < dim; ++d) {
+      int ex = s->n[0] + (d == 0), ey = s->n[1] + (d == 1), ez = s->n[2] + (d == 2);
+      for (int k = 0; k < ez; ++k) for (int j = 0; j < ey; ++j) for (int i = 0; i < ex; ++i) {
+        size_t f = fidx(s, d, i, j, k);
+        if (s->ftype[f] != FT_BOUND) continue;
+        const int side = (int)s->fside[f];
+        if (side >= 6) continue;   /* faces of the rigid box are walls */
+        long cm, cp; face_cells(s, d, i, j, k, &cm, &cp);
+        const int id = (cm >= 0) ? 0 : 1;
+        const long cc = id == 0 ? cm : cp;
+        if (s->bckind[side] == HG_BC_OUTLET) {
+          const double factor = (id == 0 ? 1. : -1.);
+          if (!pass) {
+            double dot = 0.;
+            for (int c = 0; c < dim; ++c) { s->outvel[c][f] = s->u[L_IC][c][cc]; dot += s->outvel[c][f] * (c == d ? s->area[d] : 0.); }
+            outlet += dot * factor;
+            area += s->area[d];
+          } else {
+            for (int c = 0; c < dim; ++c) s->outvel[c][f] = s->outvel[c][f] + ((c == d ? s->area[d] / s->area[d] : 0. / s->area[d]) * corr) * factor;
+          }
+        } else if (s->bckind[side] == HG_BC_INLET && !pass) {
+          const double factor = (id == 0 ? -1. : 1.);
+          double dot = 0.;
+          for (int c = 0; c < dim; ++c) dot += s->bcvel[side][c] * (c == d ? s->area[d] : 0.);
+          inlet += dot * factor;
+        }
+      }
+    }
+    /* + sum of volume_source * V over the cells: zero sources */
+  }
+}
+
 int ho_fluid_make_iteration(ho_handle s) {                           /* fluid.hpp:814-1158 */
   const int dim = s->dim;
   const hg_config* cfg = &s->cfg;
@@ -456,6 +504,7 @@ int ho_fluid_make_iteration(ho_handle s) {                           /* fluid.hp
   memcpy(pprev, pcurr, s->nc * sizeof(double));                      /* :815-818 */
   memcpy(s->F[L_IP], s->F[L_IC], s->nf * sizeof(double));
   const double* Fprev = s->F[L_IP];
+  update_outlet(s);                                                  /* :820-821 */
 
   /* CalcExtForce fluid.hpp:602-631 */
   for (int d = 0; d < dim; ++d) interp(s, s->force[d], K_NEUMANN0, 0, s->ffe[d]);
@@ -908,9 +957,6 @@ int ho_create(const hg_config* cfg, ho_handle* out) {
       cfg->simpler || cfg->force_geometric_average) {
     snprintf(g_err, sizeof g_err, "unsupported configuration"); return HG_ERR_INVALID;
   }
-  for (int sd = 0; sd < 2 * cfg->dim; ++sd) if (cfg->condition_kind[sd] == HG_BC_OUTLET) {
-    snprintf(g_err, sizeof g_err, "outlet condition not supported"); return HG_ERR_INVALID;
-  }
   struct ho_state* s = (struct ho_state*)calloc(1, sizeof *s);
   s->cfg = *cfg;
   const int dim = s->dim = cfg->dim;
@@ -976,6 +1022,8 @@ int ho_create(const hg_config* cfg, ho_handle* out) {
     for (int ph = 0; ph < HG_MAX_PHASES; ++ph) s->pd[ph][l] = dalloc(nc);
   }
   for (int ph = 0; ph < HG_MAX_PHASES; ++ph) { s->vf[ph] = dalloc(nc); s->pd_inlet[ph] = dalloc(nf); }
+  for (int d = 0; d < 3; ++d) s->outvel[d] = dalloc(nf);
+  for (int sd = 0; sd < 2 * dim; ++sd) if (cfg->condition_kind[sd] == HG_BC_OUTLET) s->any_outlet = 1;
   s->rho_raw = dalloc(nc); s->rho = dalloc(nc); s->mu = dalloc(nc); s->kc = dalloc(nc);
   s->qvol = dalloc(nc); s->qmass = dalloc(nc); s->tsrc = dalloc(nc);
   s->muf = dalloc(nf); s->ffp = dalloc(nf); s->dc = dalloc(nc); s->dfc = dalloc(nf); s->Fs = dalloc(nf); s->cf = dalloc(nf);
@@ -1058,6 +1106,7 @@ int ho_destroy(ho_handle s) {
     for (int ph = 0; ph < HG_MAX_PHASES; ++ph) free(s->pd[ph][l]);
   }
   for (int ph = 0; ph < HG_MAX_PHASES; ++ph) { free(s->vf[ph]); free(s->pd_inlet[ph]); }
+  for (int d = 0; d < 3; ++d) free(s->outvel[d]);
   free(s->rho_raw); free(s->rho); free(s->mu); free(s->kc); free(s->qvol); free(s->qmass); free(s->tsrc);
   free(s->muf); free(s->ffp); free(s->dc); free(s->dfc); free(s->Fs); free(s->cf);
   free(s->pc); free(s->rhs); free(s->corr); free(s->w1); free(s->wf); free(s->kf);

@@ -98,6 +98,11 @@ GOLDEN_CASES = {
     # interface sharpening (advection.hpp:479-529), with and without the directional split
     "rt3d_8_sharp_split": (rt3d(8, sharp=0.05, tvd_split=1), 3),
     "dam2d_32x16_sharp": (broken_dam_2d(32, 16, sharp=0.02, lu_relaxed_num_iters_limit=40), 3),
+    # outlet conditions with the outlet mass balance (fluid.hpp:309-336, 542-600)
+    "channel2d_32x16_outlet": (cavity(16, Nx=32, Ny=16, B=(2, 1, 1), condition_top="wall 0 0 0", condition_left="inlet 1 0 0",
+                                      condition_right="outlet", num_iterations_limit=5, lu_relaxed_num_iters_limit=60,
+                                      viscosity_0=0.01), 3),
+    "rt3d_8_inlet_outlet": (rt3d(8, condition_left="inlet 0.05 0 0", condition_right="outlet"), 2),
     "thermal2d_24x12_vellur_heatgs": (thermal_2d(24, 12, linear_solver_velocity="lu_relaxed", linear_solver_heat="gauss_seidel",
                                                  lu_relaxed_num_iters_limit=12, lu_relaxed_relaxation_factor=0.7), 2),
 }

@@ -14,3 +14,4 @@ import json,sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 print("ms/step %.2f gs %.2f ms lu %.2f ms frac %.3f e2e %.1f cpu %s asconf %s" % (d["ms_per_step"], d["roofline"]["avg_launch_ms"], d["roofline"]["lu_avg_solve_ms"] or 0, d["roofline"]["whole_step"]["frac"], d["e2e"]["ms_per_step"], (d.get("cpu_baseline") or {}).get("value"), (d.get("as_configured") or {}).get("ms_per_step")))
 PY
+bash tools/gpu_ncu_multi.sh ${TAG}_fast "k_f[a-e]_" 12 6
