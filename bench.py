@@ -300,6 +300,16 @@ def run_b200(args, rank, local_rank, world):
     gs_n, gs_ms = h.profile_read(0)
     lu_n, lu_ms = h.profile_read(1)
     h.profile_enable(False)
+    if os.environ.get("HYDRO_BENCH_TIMERS") and rank == 0:
+        # per-section device times of three more steps (events around every section: serialising, not part of any number)
+        h.timers_enable(True)
+        for _ in range(3):
+            h.step()
+        print("timers (s per 3 steps):", {k: round(v, 5) for k, v in sorted(h.timers().items())}, file=sys.stderr)
+        h.timers_enable(False)
+    elif os.environ.get("HYDRO_BENCH_TIMERS"):
+        for _ in range(3):
+            h.step()
     if world > 1 and os.environ.get("HYDRO_BENCH_RANKS"):
         print("rank %d: step %.2f ms, gs %.2f ms x %d, lu %.2f ms x %d" % (rank, h.event_elapsed_ms(0, 1) / K, gs_ms / max(gs_n, 1), gs_n, lu_ms / max(lu_n, 1), lu_n), file=sys.stderr)
     if os.environ.get("HYDRO_GT_CLOCK"):
