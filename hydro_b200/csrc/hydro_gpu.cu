@@ -438,23 +438,24 @@ static int run_jacobi(hg_state* s, double* const* rows, const double* D, const d
   if (int rc = ensure_sweep_capacity(s, check + 2)) return rc;
   double* xc = s->pc; double* xo = s->w2;
   CK(cudaMemsetAsync(xc, 0, s->nc * sizeof(double), s->st));
-  auto sweeps = [&](int nsw) {
+  auto sweeps = [&](int nsw) -> int {
     double* a_ = xc; double* b_ = xo;
     for (int q = 0; q < nsw; ++q) {
       JacArgs a; for (int t = 0; t < 7; ++t) a.A[t] = rows ? rows[t] : nullptr;
       a.D = D; a.R = R; a.xin = a_; a.xout = b_; a.diff = s->diffs + q; a.omega = omega;
+      if (s->world > 1) { if (int rc = slab_exchange(s, {a_}, 1)) return rc; }   // slabs: the iterate's values across the interfaces
       DIMSEL(s, k_jacobi_sweep, nblk(s->nc), 256, s->geo, a);
       std::swap(a_, b_);
     }
+    return 0;
   };
   int done = 0;
   for (;;) {
     const int nb = std::min(check, limit + 1 - done);
     CK(cudaMemcpyAsync(s->PPsave, xc, s->nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
     CK(cudaMemsetAsync(s->diffs, 0, nb * sizeof(double), s->st));
-    sweeps(nb);
-    CK(cudaMemcpyAsync(s->hdiffs, s->diffs, nb * sizeof(double), cudaMemcpyDeviceToHost, s->st));
-    CK(cudaStreamSynchronize(s->st));
+    if (int rc = sweeps(nb)) return rc;
+    if (int rc = slab_reduce(s, s->diffs, nb, 0, s->hdiffs)) return rc;   // (one GPU: a plain read-back)
     int nsw = -1;
     for (int q = 0; q < nb; ++q) {
       const int k = done + q;
@@ -465,7 +466,7 @@ static int run_jacobi(hg_state* s, double* const* rows, const double* D, const d
     if (nsw != nb) {
       CK(cudaMemcpyAsync(xc, s->PPsave, s->nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
       CK(cudaMemsetAsync(s->diffs, 0, nb * sizeof(double), s->st));
-      sweeps(nsw);
+      if (int rc = sweeps(nsw)) return rc;
     }
     if (nsw & 1) std::swap(xc, xo);
     break;
@@ -1471,8 +1472,8 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     return fail_create(nullptr, HG_ERR_INVALID, "bad world_size / rank");
   if (cfg->world_size > 1 && (cfg->dim != 3 || cfg->Nz < 2 * cfg->world_size))
     return fail_create(nullptr, HG_ERR_INVALID, "z-slab decomposition needs dim 3 and at least 2 planes per rank");
-  if (cfg->world_size > 1 && cfg->linear_solver_pressure != HG_LS_GAUSS_SEIDEL)
-    return fail_create(nullptr, HG_ERR_INVALID, "multi-GPU slabs support gauss_seidel for the pressure system");
+  if (cfg->world_size > 1 && cfg->linear_solver_pressure != HG_LS_GAUSS_SEIDEL && cfg->linear_solver_pressure != HG_LS_JACOBI)
+    return fail_create(nullptr, HG_ERR_INVALID, "multi-GPU slabs support gauss_seidel and jacobi for the pressure system");
   if (cfg->world_size > SLAB_MAX_WORLD) return fail_create(nullptr, HG_ERR_INVALID, "world_size too large");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)

@@ -33,7 +33,7 @@ def devices_for(world):
 
 @pytest.mark.parametrize("kernel", ["hyperplane", "tiled"])
 @pytest.mark.parametrize("case,world", [("rt3d_16", 2), ("rt3d_20x12x17", 3), ("dam3d_32x10x12", 2), ("rt3d_tol", 2),
-                                        ("rt3d_stf_20x12x16", 2), ("thermal3d_24x12x15", 3)])
+                                        ("rt3d_stf_20x12x16", 2), ("thermal3d_24x12x15", 3), ("rt3d_jacobi_16x12x14", 2)])
 def test_slabs_equal_single_gpu(case, world, kernel, monkeypatch):
     # hyperplane: the neighbour-linked hyperplane kernels on both sides; tiled: the box-dataflow kernels (k_gs_tiled,
     # k_lu_tiled) with tagged interface values between the slabs -- all bitwise equal to the single-GPU run
@@ -48,6 +48,9 @@ def test_slabs_equal_single_gpu(case, world, kernel, monkeypatch):
          "thermal3d_24x12x15": cases.rt3d(8, Nx=24, Ny=12, Nz=15, lu_relaxed_num_iters_limit=15, heat_enable=1,
                                           heat_box_lb=(-1., -1., -1.), heat_box_rt=(2., 0.01, 2.), heat_box_temperature=1.,
                                           conductivity_0=0.01, conductivity_1=0.05),
+         "rt3d_jacobi_16x12x14": cases.rt3d(8, Nx=16, Ny=12, Nz=14, linear_solver_pressure="jacobi", lu_relaxed_relaxation_factor=0.9,
+                                            lu_relaxed_num_iters_limit=60, lu_relaxed_tolerance=1e-6, convergence_tolerance=0.0,
+                                            num_iterations_limit=3),
          "rt3d_tol": cases.rt3d(12, fixed_work=False, lu_relaxed_num_iters_limit=200, lu_relaxed_tolerance=1e-6,
                                num_iterations_limit=3, pressure_sweeps_per_check=32)}[case]
     fields = FIELDS + (["TEMPERATURE"] if p.get("heat_enable") else []) + (["STFORCE_X", "STFORCE_Y", "STFORCE_Z"] if p.get("sigma") else [])
