@@ -51,7 +51,9 @@ class HgConfig(C.Structure):
         ("heat_box_lb", d3), ("heat_box_rt", d3), ("heat_box_temperature", C.c_double),
         ("heat_relaxation_factor", C.c_double), ("time_second_order_heat", C.c_int),
         ("world_size", C.c_int), ("rank", C.c_int), ("device", C.c_int),
-        ("pressure_sweeps_per_check", C.c_int), ("solver_ctas", C.c_int), ("reserved", C.c_int * 6),
+        ("pressure_sweeps_per_check", C.c_int), ("solver_ctas", C.c_int),
+        ("enable_settling", C.c_int * HG_MAX_PHASES), ("velocity_is_carrier", C.c_int), ("bubble_radius", dP),
+        ("reserved", C.c_int * 6),
     ]
 
 
@@ -486,6 +488,8 @@ class Params(dict):
             c.viscosity[i] = float(p.get("viscosity_%d" % i, 1.0))
             c.conductivity[i] = float(p.get("conductivity_%d" % i, 1.0))
             c.initial_volume_fraction[i] = float(p.get("initial_volume_fraction_%d" % i, 0.0))
+            c.enable_settling[i] = int(bool(int(p.get("enable_settling_%d" % i, 0))))
+            c.bubble_radius[i] = float(p.get("bubble_radius_%d" % i, 0.0)) if c.enable_settling[i] else 0.0
         for name in ("initial_volume_fraction_smooth_times", "dt_auto", "fluid_enable", "advection_enable",
                      "num_iterations_limit", "time_second_order", "simpler", "force_geometric_average",
                      "lu_relaxed_num_iters_limit", "density_smooth_times", "viscosity_smooth_times",
@@ -541,13 +545,14 @@ def reject_unsupported(p):
     for k in ("meshvel_auto", "imgu_init", "imgv_init", "img_init"):
         if k in p:
             raise ValueError("%s is not on the GPU path" % k)
-    for i in range(HG_MAX_PHASES):
-        if truthy("enable_settling_%d" % i):
-            raise ValueError("phase slip (enable_settling_%d) is not on the GPU path" % i)
+    if truthy("velocity_is_carrier"):
+        raise ValueError("velocity_is_carrier 1 (mixture volume source) is not on the GPU path")
+    if float(p.get("antidiffusion_factor", 0.0)) != 0.0:
+        raise ValueError("antidiffusion_factor != 0 is not on the GPU path")
 
 
-_DOUBLE_KEYS = {"initial_sin_lambda", "initial_sin_phase", "pressure_fixed_value", "T", "dt",
+_DOUBLE_KEYS = {"bubble_radius_0", "bubble_radius_1", "bubble_radius_2", "antidiffusion_factor", "initial_sin_lambda", "initial_sin_phase", "pressure_fixed_value", "T", "dt",
                 "initial_volume_fraction_0", "initial_volume_fraction_1", "initial_volume_fraction_2"}
-_BOOL_KEYS = {"dt_auto", "deforming_velocity", "radiation_enable", "heat_enable", "time_second_order_heat",
+_BOOL_KEYS = {"enable_settling_0", "enable_settling_1", "enable_settling_2", "velocity_is_carrier", "dt_auto", "deforming_velocity", "radiation_enable", "heat_enable", "time_second_order_heat",
               "fluid_enable", "advection_enable", "tvd_split", "time_second_order", "simpler",
               "force_geometric_average", "compressible_enable", "initial_pois", "no_output", "no_mesh_output"}

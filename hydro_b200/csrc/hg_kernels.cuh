@@ -732,6 +732,85 @@ __global__ void __launch_bounds__(256, 4) k_sharpen(Geo g, const double* __restr
   out[c] = v;
 }
 
+// ---------------------------------------------------------------- phase slip (CalcPhaseVelocitySlip, hydro2d.hpp:1030-1122)
+// velocity_is_carrier 0: Stokes settling velocity of every enabled phase relative to the carrier, made relative to the mixture
+// (cell vectors slipv[phase][component]); slip flux on the inner faces, corrected to zero volume-weighted average.
+struct SlipArgs {
+  int np; int enable[3]; double radius[3], density[3], gravity[3];
+  const double* vf[3]; const double* rho_raw; const double* mu;
+  double* slipv[3][3];       // cell
+  double* fslip[3];          // face
+};
+template <int DIM>
+__global__ void __launch_bounds__(256) k_slip_cell(Geo g, SlipArgs a) {
+  CELL_LOOP_PROLOG(g)
+  (void)i; (void)j; (void)k;
+  double rel[3][3];
+#pragma unroll
+  for (int ph = 0; ph < 3; ++ph)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) rel[ph][d] = 0.;
+  const double md = a.rho_raw[c], mv = a.mu[c];
+#pragma unroll
+  for (int ph = 0; ph < 3; ++ph) {
+    if (ph < a.np && a.enable[ph]) {
+      const double pc = a.vf[ph][c];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d)
+        rel[ph][d] = (pc < 0.01 || pc > 0.99) ? 0. : a.gravity[d] * (a.density[ph] - md) * (a.radius[ph] * a.radius[ph]) / (18. * mv);
+    }
+  }
+  double carrier[3] = {0., 0., 0.};
+#pragma unroll
+  for (int ph = 0; ph < 3; ++ph) if (ph < a.np) {
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) carrier[d] += rel[ph][d] * a.vf[ph][c];
+  }
+#pragma unroll
+  for (int ph = 0; ph < 3; ++ph) if (ph < a.np) {
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) a.slipv[ph][d][c] = rel[ph][d] - carrier[d];
+  }
+}
+template <int DIM>
+DV void slip_face(const Geo& g, const SlipArgs& a, int d, int fi, int fj, int fk) {
+  const FaceInfo f = face_info<DIM>(g, d, fi, fj, fk);
+  const long long fx = fidx(g, d, fi, fj, fk);
+  if (f.type != FT_INNER) {
+    for (int ph = 0; ph < a.np; ++ph) a.fslip[ph][fx] = 0.;
+    return;
+  }
+  double fs[3] = {0., 0., 0.};
+#pragma unroll
+  for (int ph = 0; ph < 3; ++ph) if (ph < a.np) {
+    double dot = 0.;
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) dot += (a.slipv[ph][c][f.cm] * (1. - 0.5) + a.slipv[ph][c][f.cp] * 0.5) * (c == d ? g.area[d] : 0.);
+    fs[ph] = dot;
+  }
+  double aver = 0.;
+#pragma unroll
+  for (int ph = 0; ph < 3; ++ph) if (ph < a.np) aver += (a.vf[ph][f.cm] * (1. - 0.5) + a.vf[ph][f.cp] * 0.5) * fs[ph];
+#pragma unroll
+  for (int ph = 0; ph < 3; ++ph) if (ph < a.np) a.fslip[ph][fx] = fs[ph] - aver;
+}
+template <int DIM>
+__global__ void __launch_bounds__(256) k_slip_face(Geo g, SlipArgs a) {
+  CELL_LOOP_PROLOG(g)
+  (void)c;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    slip_face<DIM>(g, a, d, i, j, k);
+    const int x = d == 0 ? i : (d == 1 ? j : k);
+    if (x == g.n[d] - 1) slip_face<DIM>(g, a, d, i + (d == 0), j + (d == 1), k + (d == 2));
+  }
+}
+// flux of a phase's advection = mixture flux + slip flux (advection.hpp:449-454)
+__global__ void k_face_add(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, long long n) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = a[t] + b[t];
+}
+
 // ---------------------------------------------------------------- outlet conditions (fluid.hpp:542-600)
 // Pass A (one thread per boundary face of the domain sides): every outlet face takes the velocity of its cell; the face's
 // contributions to the outlet flux, the outlet area and the inlet flux are stored at the face's position in the reference's

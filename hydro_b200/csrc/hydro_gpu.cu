@@ -71,6 +71,7 @@ struct hg_state {
   // [0]: radius-1 stencils (SIMPLE iteration), [1]: radius 2 (advection)
   bool fast = false; unsigned char* slow = nullptr; int* slow_list = nullptr; int nslow = 0;
   unsigned char* slow2 = nullptr; int* slow2_list = nullptr; int nslow2 = 0;
+  bool any_slip = false; double* slipv[HG_MAX_PHASES][3] = {}; double* fslip[HG_MAX_PHASES] = {};   // phase slip
   double* outvel = nullptr; double* outpart = nullptr; bool any_outlet = false; int out_blocks = 0; long long out_terms = 0;   // outlet conditions
   double* resid = nullptr;    // per-iteration convergence indicators of the current step (device, 4096)
   double* scal = nullptr;     // device scalars: [0] resid, [1] auto dt, [2..] stat (36), then diffs
@@ -825,6 +826,18 @@ extern "C" int hg_update_properties(hg_handle s) {
       CK(cudaMemcpyAsync(s->force[d], s->w1, s->nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
     }
   }
+  if (s->any_slip) {   // CalcPhaseVelocitySlip (hydro2d.hpp:1422)
+    SlipArgs q; q.np = c.num_phases;
+    for (int ph = 0; ph < 3; ++ph) {
+      q.enable[ph] = ph < c.num_phases ? c.enable_settling[ph] : 0; q.radius[ph] = c.bubble_radius[ph]; q.density[ph] = c.density[ph];
+      q.vf[ph] = s->vf[ph] ? s->vf[ph] : s->zero; q.fslip[ph] = s->fslip[ph];
+      for (int d = 0; d < 3; ++d) q.slipv[ph][d] = s->slipv[ph][d];
+    }
+    for (int d = 0; d < 3; ++d) q.gravity[d] = c.gravity[d];
+    q.rho_raw = s->rho_raw; q.mu = s->mu;
+    DIMSEL(s, k_slip_cell, nblk(s->nc), 256, s->geo, q);
+    DIMSEL(s, k_slip_face, nblk(s->nc), 256, s->geo, q);
+  }
   // slabs: face values of density, viscosity and force are taken across the slab interfaces
   XCH(s, 1, s->rho, s->mu, s->force[0], s->force[1], s->dim > 2 ? s->force[2] : nullptr, c.heat_enable ? s->kc : nullptr);
   tpop(s);
@@ -1220,6 +1233,9 @@ extern "C" int hg_advection_step(hg_handle s) {   // advection.hpp:417-545
   const int num_stages = c.tvd_split ? s->dim : 1;
   for (int ph = 0; ph < c.num_phases; ++ph) {
     // StartStep: time_prev = time_curr (values); the update reads time_curr and writes a fresh buffer
+    // flux of this phase: mixture flux + its slip flux (advection.hpp:449-454); F* of the SIMPLE iteration is free here
+    const double* Fadv = s->F[L_TC];
+    if (s->any_slip) { LAUNCH(s, k_face_add, nblk(s->nf), 256, s->F[L_TC], s->fslip[ph], s->Fs, s->nf); Fadv = s->Fs; }
     double* src = s->pd[ph][L_TC];
     CK(cudaMemcpyAsync(s->pd[ph][L_TP], src, s->nc * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
     double* bufs[2] = {s->pd[ph][L_IC], s->pd[ph][L_IP]};
@@ -1229,9 +1245,9 @@ extern "C" int hg_advection_step(hg_handle s) {   // advection.hpp:417-545
       out = bufs[stage % 2];
       XCH(s, 2, const_cast<double*>(in));
       if (s->fast) {
-        k_fe_advect<<<fast_grid(s), FT_THREADS, 0, s->st>>>(s->geo, s->slow2, in, s->F[L_TC], s->dt_adv, num_stages, stage, out); ++s->launches;
-        if (s->nslow2) { k_advect<3><<<nblk(s->nslow2), 256, 0, s->st>>>(list_geo(s, 2), in, s->pd_init[ph], s->F[L_TC], s->dt_adv, num_stages, stage, out); ++s->launches; }
-      } else DIMSEL(s, k_advect, nblk(s->nc), 256, s->geo, in, s->pd_init[ph], s->F[L_TC], s->dt_adv, num_stages, stage, out);
+        k_fe_advect<<<fast_grid(s), FT_THREADS, 0, s->st>>>(s->geo, s->slow2, in, Fadv, s->dt_adv, num_stages, stage, out); ++s->launches;
+        if (s->nslow2) { k_advect<3><<<nblk(s->nslow2), 256, 0, s->st>>>(list_geo(s, 2), in, s->pd_init[ph], Fadv, s->dt_adv, num_stages, stage, out); ++s->launches; }
+      } else DIMSEL(s, k_advect, nblk(s->nc), 256, s->geo, in, s->pd_init[ph], Fadv, s->dt_adv, num_stages, stage, out);
       in = out;
     }
     if (std::fabs(c.sharp) > 1e-10) {   // interface sharpening, once per field after the stages (advection.hpp:479-529)
@@ -1240,7 +1256,7 @@ extern "C" int hg_advection_step(hg_handle s) {   // advection.hpp:417-545
       P3 gc; CP3 gcc; for (int d = 0; d < 3; ++d) { gc.p[d] = s->G[d]; gcc.p[d] = s->G[d]; }
       DIMSEL(s, k_grad_pd, nblk(s->nc), 256, s->geo, out, s->pd_init[ph], gc);
       XCH(s, 1, s->G[0], s->G[1], s->dim > 2 ? s->G[2] : nullptr);
-      DIMSEL(s, k_sharpen, nblk(s->nc), 256, s->geo, out, s->pd_init[ph], gcc, s->F[L_TC], s->dt_adv, c.sharp, c.density[ph], sharpened);
+      DIMSEL(s, k_sharpen, nblk(s->nc), 256, s->geo, out, s->pd_init[ph], gcc, Fadv, s->dt_adv, c.sharp, c.density[ph], sharpened);
       out = sharpened;
     }
     // FinishStep: time_curr = iter_curr
@@ -1461,6 +1477,9 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
     return fail_create(nullptr, HG_ERR_INVALID, "bad mesh size / dim");
   if (cfg->num_phases < 1 || cfg->num_phases > HG_MAX_PHASES) return fail_create(nullptr, HG_ERR_INVALID, "num_phases must be 1..3");
   if (cfg->simpler) return fail_create(nullptr, HG_ERR_INVALID, "simpler 1 is not on the GPU path");
+  if (cfg->velocity_is_carrier) return fail_create(nullptr, HG_ERR_INVALID, "velocity_is_carrier 1 is not on the GPU path");
+  for (int ph = 0; ph < cfg->num_phases; ++ph)
+    if (cfg->enable_settling[ph] && cfg->world_size > 1) return fail_create(nullptr, HG_ERR_INVALID, "multi-GPU slabs: phase slip is not decomposed");
   if (cfg->force_geometric_average) return fail_create(nullptr, HG_ERR_INVALID, "force_geometric_average 1 is not on the GPU path");
   for (int sd = 0; sd < 2 * cfg->dim; ++sd)
     if (cfg->condition_kind[sd] == HG_BC_OUTLET && cfg->world_size > 1) return fail_create(nullptr, HG_ERR_INVALID, "multi-GPU slabs: outlet conditions are not decomposed");
@@ -1576,6 +1595,13 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
   }
   bool ok = true;
   for (int sd = 0; sd < 2 * dim; ++sd) if (cfg->condition_kind[sd] == HG_BC_OUTLET) s->any_outlet = true;
+  for (int ph = 0; ph < cfg->num_phases; ++ph) if (cfg->enable_settling[ph]) s->any_slip = true;
+  if (s->any_slip) {
+    for (int ph = 0; ph < cfg->num_phases && ok; ++ph) {
+      ok = dalloc(s, &s->fslip[ph], s->nf) == 0;
+      for (int d = 0; d < dim && ok; ++d) { double* q = nullptr; ok = dalloc(s, &q, s->nxy * (s->n[2] + 2 * HG_HALO)) == 0; s->slipv[ph][d] = q ? q + HG_HALO * s->nxy : nullptr; }
+    }
+  }
   if (s->any_outlet) {   // velocities of the outlet faces: [side][component][face of the side], zero at construction (OutletAuto)
     const long long pl = std::max({(long long)s->n[1] * s->n[2], (long long)s->n[0] * s->n[2], dim > 2 ? (long long)s->n[0] * s->n[1] : 0LL});
     g.outplane = pl;

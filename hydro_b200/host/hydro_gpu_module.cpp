@@ -111,7 +111,9 @@ class hydro_gpu : public TModule {
     for (const char* k : {"meshvel_auto", "imgu_init", "imgv_init", "img_init"})
       if (P_string.exist(k)) throw std::runtime_error(std::string("hydro_gpu: ") + k + " is not on the GPU path");
     for (int i = 0; i < c.num_phases; ++i)
-      if (flag("enable_settling_" + IntToStr(i))) throw std::runtime_error("hydro_gpu: phase slip (enable_settling) is not on the GPU path");
+      if (flag("enable_settling_" + IntToStr(i))) { c.enable_settling[i] = 1; c.bubble_radius[i] = P_double["bubble_radius_" + IntToStr(i)]; }
+    if (flag("velocity_is_carrier")) throw std::runtime_error("hydro_gpu: velocity_is_carrier 1 is not on the GPU path");
+    if (P_double.exist("antidiffusion_factor") && P_double["antidiffusion_factor"] != 0.) throw std::runtime_error("hydro_gpu: antidiffusion_factor is not on the GPU path");
     c.advection_dt_factor = P_double["advection_dt_factor"]; c.tvd_split = P_bool["tvd_split"]; c.sharp = P_double["sharp"];
     c.heat_enable = P_bool["heat_enable"]; c.temperature_initial = P_double["temperature_initial"];
     vec("heat_box_lb", c.heat_box_lb); vec("heat_box_rt", c.heat_box_rt);

@@ -143,6 +143,11 @@ typedef struct hg_config {
   /* execution options */
   int pressure_sweeps_per_check;   /* 0 = default */
   int solver_ctas;                 /* 0 = one CTA per SM; >0 limits the persistent solver grids (ranks sharing a device) */
+  /* phase slip (Stokes settling relative to the mixture, hydro<Mesh>::CalcPhaseVelocitySlip, hydro2d.hpp:1030-1122):
+   * enable_settling_<i>, bubble_radius_<i>; velocity_is_carrier 1 (a volume source) is not on the GPU path */
+  int enable_settling[HG_MAX_PHASES];
+  int velocity_is_carrier;
+  double bubble_radius[HG_MAX_PHASES];
   int reserved[6];
 } hg_config;
 

@@ -38,6 +38,9 @@ struct ho_state {
   signed char* fside;     /* boundary faces: index into bcvel (0..5 sides, 6 box) */
   unsigned char* ftdir;   /* temperature: 1 = Dirichlet (heat box) */
   double bcvel[7][3];
+  double* slipv[HG_MAX_PHASES][3]; /* v_fc_velocity_slip */
+  double* fslip[HG_MAX_PHASES];    /* v_ff_volume_flux_slip */
+  int any_slip;
   double* outvel[3];      /* velocity of the outlet faces (OutletAuto, fluid.hpp:318-336), face-field sized, zero at construction */
   int any_outlet;
   int bckind[7];
@@ -704,6 +707,9 @@ static void advection_iteration(struct ho_state* s) {                /* advectio
   const double* F = s->F[L_IC];                                      /* hydro2d.hpp:596 */
   for (int ph = 0; ph < s->cfg.num_phases; ++ph) {
     double* prev = s->pd[ph][L_IP]; double* curr = s->pd[ph][L_IC];
+    /* ff_volume_flux = mixture flux + slip flux of the phase (advection.hpp:449-454) */
+    const double* Fa = F;
+    if (s->any_slip) { for (size_t f = 0; f < s->nf; ++f) s->cf[f] = F[f] + s->fslip[ph][f]; Fa = s->cf; }
     memcpy(prev, curr, s->nc * sizeof(double));
     int num_stages = s->cfg.tvd_split ? dim : 1;
     for (int stage = 0; stage < num_stages; ++stage) {
@@ -720,13 +726,13 @@ static void advection_iteration(struct ho_state* s) {                /* advectio
           long P, E; face_cells(s, d, i, j, k, &P, &E);
           if (s->ftype[f] == FT_INNER) {
             double du = curr[E] - curr[P];
-            if (F[f] > 1e-8) {
+            if (Fa[f] > 1e-8) {
               double pq = -4. * (g[d][P] * (-0.5 * s->h[d])) - du;
               double sb = 0.;
               if (du > 0. && pq > 0.) sb = fmax(fmin(2 * du, pq), fmin(du, 2 * pq));
               else if (du < 0. && pq < 0.) sb = -fmax(fmin(-2 * du, -pq), fmin(-du, -2 * pq));
               fu[f] = curr[P] + 0.5 * sb;
-            } else if (F[f] < -1e-8) {
+            } else if (Fa[f] < -1e-8) {
               double pq = 4. * (g[d][E] * (0.5 * s->h[d])) - du;
               double sb = 0.;
               if (du > 0. && pq > 0.) sb = fmax(fmin(2 * du, pq), fmin(du, 2 * pq));
@@ -744,7 +750,7 @@ static void advection_iteration(struct ho_state* s) {                /* advectio
         for (int q = 0; q < 2 * dim; ++q) {
           if ((q / 2) % num_stages != stage) continue;
           size_t f = nface(s, i, j, k, q);
-          fsum += fu[f] * F[f] * ((q & 1) ? 1. : -1.);
+          fsum += fu[f] * Fa[f] * ((q & 1) ? 1. : -1.);
         }
         curr[c] += -s->dt_adv / s->vol * fsum;
       }
@@ -769,7 +775,7 @@ static void advection_iteration(struct ho_state* s) {                /* advectio
           if (nrm < 1.) continue;                                  /* th = 1 */
           double nf = 0.;
           for (int c = 0; c < dim; ++c) { n[c] /= (nrm + 1e-6); nf += n[c] * (c == d ? 1. : 0.); }   /* n.dot(GetNormal) */
-          const double uf = F[f];
+          const double uf = Fa[f];
           const double epsh = s->cfg.sharp * s->area[d];
           ff[f] = fabs(uf * nf) * nf * (epsh * nrm - af[f] * (1. - af[f] / am));
         }
@@ -813,6 +819,42 @@ int ho_heat_step(ho_handle s) {                                      /* heat.hpp
 }
 
 /* ------------------------------------------------------- fluid properties */
+/* CalcPhaseVelocitySlip, hydro2d.hpp:1030-1122 (velocity_is_carrier 0): Stokes settling velocity of every phase relative
+ * to the carrier, made relative to the mixture; slip flux on the inner faces, corrected to zero volume-weighted average */
+static void calc_slip(struct ho_state* s) {
+  if (!s->any_slip) return;
+  const hg_config* cfg = &s->cfg;
+  const int np = cfg->num_phases, dim = s->dim;
+  for (size_t c = 0; c < s->nc; ++c) {
+    double rel[HG_MAX_PHASES][3] = {{0.}};
+    for (int i = 0; i < np; ++i) {
+      if (!cfg->enable_settling[i]) continue;
+      const double pc = s->vf[i][c], md = s->rho_raw[c], mv = s->mu[c], pdn = cfg->density[i];
+      for (int d = 0; d < dim; ++d)
+        rel[i][d] = (pc < 0.01 || pc > 0.99) ? 0. : cfg->gravity[d] * (pdn - md) * (cfg->bubble_radius[i] * cfg->bubble_radius[i]) / (18. * mv);
+    }
+    double carrier[3] = {0., 0., 0.};
+    for (int i = 0; i < np; ++i) for (int d = 0; d < dim; ++d) carrier[d] += rel[i][d] * s->vf[i][c];
+    for (int i = 0; i < np; ++i) for (int d = 0; d < dim; ++d) s->slipv[i][d][c] = rel[i][d] - carrier[d];
+  }
+  for (int d = 0; d < dim; ++d) {
+    int ex = s->n[0] + (d == 0), ey = s->n[1] + (d == 1), ez = s->n[2] + (d == 2);
+    for (int k = 0; k < ez; ++k) for (int j = 0; j < ey; ++j) for (int i = 0; i < ex; ++i) {
+      size_t f = fidx(s, d, i, j, k);
+      if (s->ftype[f] != FT_INNER) { for (int ph = 0; ph < np; ++ph) s->fslip[ph][f] = 0.; continue; }
+      long cm, cp; face_cells(s, d, i, j, k, &cm, &cp);
+      for (int ph = 0; ph < np; ++ph) {
+        double dot = 0.;
+        for (int c = 0; c < dim; ++c) dot += (s->slipv[ph][c][cm] * (1. - 0.5) + s->slipv[ph][c][cp] * 0.5) * (c == d ? s->area[d] : 0.);
+        s->fslip[ph][f] = dot;
+      }
+      double aver = 0.;
+      for (int ph = 0; ph < np; ++ph) aver += (s->vf[ph][cm] * (1. - 0.5) + s->vf[ph][cp] * 0.5) * s->fslip[ph][f];
+      for (int ph = 0; ph < np; ++ph) s->fslip[ph][f] -= aver;
+    }
+  }
+}
+
 int ho_update_properties(ho_handle s) {                              /* hydro2d.hpp:1404-1430 */
   const hg_config* cfg = &s->cfg;
   const int np = cfg->num_phases, dim = s->dim;
@@ -860,6 +902,7 @@ int ho_update_properties(ho_handle s) {                              /* hydro2d.
     smooth(s, s->force[d], cfg->force_smooth_times, s->w1, s->wf, s->corr);
     memcpy(s->force[d], s->w1, s->nc * sizeof(double));
   }
+  calc_slip(s);                                                      /* :1422 */
   return 0;
 }
 
@@ -954,7 +997,7 @@ static int inside(const double lb[3], const double rt[3], const double x[3], int
 int ho_create(const hg_config* cfg, ho_handle* out) {
   if (!cfg || !out) return HG_ERR_INVALID;
   if ((cfg->dim != 2 && cfg->dim != 3) || cfg->num_phases < 1 || cfg->num_phases > HG_MAX_PHASES ||
-      cfg->simpler || cfg->force_geometric_average) {
+      cfg->simpler || cfg->force_geometric_average || cfg->velocity_is_carrier) {
     snprintf(g_err, sizeof g_err, "unsupported configuration"); return HG_ERR_INVALID;
   }
   struct ho_state* s = (struct ho_state*)calloc(1, sizeof *s);
@@ -1023,6 +1066,7 @@ int ho_create(const hg_config* cfg, ho_handle* out) {
   }
   for (int ph = 0; ph < HG_MAX_PHASES; ++ph) { s->vf[ph] = dalloc(nc); s->pd_inlet[ph] = dalloc(nf); }
   for (int d = 0; d < 3; ++d) s->outvel[d] = dalloc(nf);
+  for (int ph = 0; ph < HG_MAX_PHASES; ++ph) { s->fslip[ph] = dalloc(nf); for (int d = 0; d < 3; ++d) s->slipv[ph][d] = dalloc(nc); if (ph < cfg->num_phases && cfg->enable_settling[ph]) s->any_slip = 1; }
   for (int sd = 0; sd < 2 * dim; ++sd) if (cfg->condition_kind[sd] == HG_BC_OUTLET) s->any_outlet = 1;
   s->rho_raw = dalloc(nc); s->rho = dalloc(nc); s->mu = dalloc(nc); s->kc = dalloc(nc);
   s->qvol = dalloc(nc); s->qmass = dalloc(nc); s->tsrc = dalloc(nc);
@@ -1107,6 +1151,7 @@ int ho_destroy(ho_handle s) {
   }
   for (int ph = 0; ph < HG_MAX_PHASES; ++ph) { free(s->vf[ph]); free(s->pd_inlet[ph]); }
   for (int d = 0; d < 3; ++d) free(s->outvel[d]);
+  for (int ph = 0; ph < HG_MAX_PHASES; ++ph) { free(s->fslip[ph]); for (int d = 0; d < 3; ++d) free(s->slipv[ph][d]); }
   free(s->rho_raw); free(s->rho); free(s->mu); free(s->kc); free(s->qvol); free(s->qmass); free(s->tsrc);
   free(s->muf); free(s->ffp); free(s->dc); free(s->dfc); free(s->Fs); free(s->cf);
   free(s->pc); free(s->rhs); free(s->corr); free(s->w1); free(s->wf); free(s->kf);

@@ -99,7 +99,7 @@ def test_product_does_not_import_oracle():
 
 @pytest.mark.parametrize("key,val", [("compressible_enable", 1), ("deforming_velocity", 1), ("radiation_enable", 1),
                                      ("chemistry", "Nadirov"), ("chem_intensity", 0.5), ("meshvel_auto", "phase0"),
-                                     ("imgu_init", "u.pgm"), ("enable_settling_1", 1)])
+                                     ("imgu_init", "u.pgm"), ("velocity_is_carrier", 1), ("antidiffusion_factor", 0.3)])
 def test_options_outside_the_gpu_path_are_rejected(key, val):
     """Options that change the reference's results (hydro2d.hpp:326-368, 1030-1217, 1294, 1387, 1511-1524) must not be
     dropped silently: Params.to_struct raises before a handle is created."""
