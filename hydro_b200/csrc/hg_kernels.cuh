@@ -34,6 +34,9 @@ struct P3 { double* p[3]; };
 struct CP3 { const double* p[3]; };
 struct P9 { double* p[9]; };
 struct P7 { double* p[7]; };
+// hyperplane-major row arrays of k_gs_tiled (Co5 / gt_co5_index in hg_gs_tiled.cuh), array 0: what a kernel of this file needs
+struct Co5Fwd { long long plane; int nxp, pad; };
+HD long long co5fwd_index(const Co5Fwd& c, int i, int j, int k) { return (long long)(i + j + k + 1 + c.pad) * c.plane + (long long)j * c.nxp + i; }
 
 // ---------------------------------------------------------------- small utilities
 __global__ void k_fill(double* a, double v, long long n) {
@@ -730,6 +733,96 @@ __global__ void __launch_bounds__(256, 4) k_sharpen(Geo g, const double* __restr
   v += dt * 0.;
   v += dt * sh / g.vol;
   out[c] = v;
+}
+
+// ---------------------------------------------------------------- SIMPLER: second pressure solve (fluid.hpp:1060-1155)
+// fc_evaluated = momentum equations (rows A, constants R of this iteration, hyperplane-major) applied to the velocity change of
+// the iteration + restored force - pressure gradient (:1073-1094)
+struct SimplerArgs {
+  const double* A[7]; const double* R[3]; const double* uc[3]; const double* up[3]; const double* fcr[3]; const double* gp[3];
+  const double* force[3]; const double* dc; const double* F; const double* p; double rc;
+  double* fev[3];
+  double* RP; double* CO; Co5Fwd co5; int out_mode;   // constants: 1 = hyperplane-major RP, 2 = array 0 of the CO5 rows
+};
+template <int DIM>
+__global__ void __launch_bounds__(256, 4) k_simpler_eval(Geo g, SimplerArgs a) {
+  CELL_LOOP_PROLOG(g)
+  const long long cs = shidx(g, i, j, k);
+  const long long off[7] = {-g.sz, -g.sy, -1, 0, 1, g.sy, g.sz};
+  const int di[7] = {0, 0, -1, 0, 1, 0, 0}, dj[7] = {0, -1, 0, 0, 0, 1, 0}, dk[7] = {-1, 0, 0, 0, 0, 0, 1};
+#pragma unroll
+  for (int n = 0; n < DIM; ++n) {
+    double ev = a.R[n][cs];
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+      if (DIM == 2 && (t == CZM || t == CZP)) continue;
+      const double coef = a.A[t][cs];
+      if (t != CD && !(cell_in(g, i + di[t], j + dj[t], k + dk[t]) && coef != 0.)) continue;   // terms of the expression only
+      const long long nb = c + off[t];
+      ev += (a.uc[n][nb] - a.up[n][nb]) * coef;
+    }
+    a.fev[n][c] = ev + (a.fcr[n][c] - a.gp[n][c]);
+  }
+}
+// ff_rhs on the cell's faces (:1099-1112), constant = -sum (:1114-1121), fixed-pressure row (:1124-1141), then
+// constant := Evaluate(pressure) over the rows of the pressure-correction system (:1143-1146)
+template <int DIM>
+__global__ void __launch_bounds__(256, 4) k_simpler_rhs(Geo g, SimplerArgs a) {
+  CELL_LOOP_PROLOG(g)
+  double cfq[6] = {0., 0., 0., 0., 0., 0.};
+  bool innerq[6] = {false, false, false, false, false, false};
+  long long nbq[6] = {0, 0, 0, 0, 0, 0};
+  double sum = 0.;
+#pragma unroll
+  for (int q = 0; q < 2 * DIM; ++q) {
+    const int d = q >> 1, o = q & 1;
+    const int fi = i + (d == 0 ? o : 0), fj = j + (d == 1 ? o : 0), fk = k + (d == 2 ? o : 0);
+    const FaceInfo f = face_info<DIM>(g, d, fi, fj, fk);
+    double frhs = 0.;
+    if (f.type == FT_INNER) {
+      double dot1 = 0., dot2 = 0.;
+#pragma unroll
+      for (int cc = 0; cc < DIM; ++cc) {
+        const double S = cc == d ? g.area[d] : 0.;
+        const double fe = a.fev[cc][f.cm] * (1. - 0.5) + a.fev[cc][f.cp] * 0.5;
+        const double ff = a.force[cc][f.cm] * (1. - 0.5) + a.force[cc][f.cp] * 0.5;
+        const double fu = a.uc[cc][f.cm] * (1. - 0.5) + a.uc[cc][f.cp] * 0.5;
+        dot1 += (fe - ff) * S;
+        dot2 += fu * S;
+      }
+      const double dfc = a.dc[f.cm] * (1. - 0.5) + a.dc[f.cp] * 0.5;
+      frhs = dot1 / dfc + (a.F[fidx(g, d, fi, fj, fk)] - dot2) / a.rc;
+      cfq[q] = face_coeff<DIM>(g, a.dc, d, f);
+      innerq[q] = true;
+      nbq[q] = o ? f.cp : f.cm;
+    }
+    sum += frhs * (o ? 1. : -1.);
+  }
+  double cst = -sum;
+  const bool ident = c == g.pfix || cell_excl(g, i, j, k);
+  if (c == g.pfix) cst = -g.pfix_value;
+  if (ident) cst += a.p[c] * 1.;
+  else {
+    double diag = cfq[0] + cfq[1]; diag = diag + cfq[2]; diag = diag + cfq[3];
+    if (DIM > 2) { diag = diag + cfq[4]; diag = diag + cfq[5]; }
+    // ascending index: z-, y-, x-, diagonal, x+, y+, z+ (terms towards the fixed-pressure cell were removed, fluid.hpp:1010)
+    const int order[7] = {4, 2, 0, -1, 1, 3, 5};
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+      const int q = order[t];
+      if (q < 0) { cst += a.p[c] * diag; continue; }
+      if (q >= 2 * DIM || !innerq[q] || nbq[q] == g.pfix) continue;
+      cst += a.p[nbq[q]] * (-cfq[q]);
+    }
+  }
+  if (a.out_mode == 2) a.CO[co5fwd_index(a.co5, i, j, k)] = cst;
+  else a.RP[shidx(g, i, j, k)] = cst;
+}
+// p_curr += p'' (:1150-1152), p'' hyperplane-major
+template <int DIM>
+__global__ void k_simpler_padd(Geo g, const double* __restrict__ PP, double* __restrict__ pcurr) {
+  CELL_LOOP_PROLOG(g)
+  pcurr[c] += PP[shidx(g, i, j, k)];
 }
 
 // ---------------------------------------------------------------- phase slip (CalcPhaseVelocitySlip, hydro2d.hpp:1030-1122)

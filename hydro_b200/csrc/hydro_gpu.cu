@@ -628,7 +628,11 @@ static void launch_pcorr(hg_state* s) {   // p' back to the natural layout, p_cu
   else k_pcorr<2><<<nblk(s->nc), 256, 0, s->st>>>(s->geo, s->PP, s->p[L_IP], alpha, s->pc, s->p[L_IC]);
   ++s->launches;
 }
-static int solve_pressure(hg_state* s) {
+// second = the SIMPLER solve (fluid.hpp:1148-1152): same rows, new constants, the result is added to the pressure unrelaxed
+static void launch_padd(hg_state* s) {
+  DIMSEL(s, k_simpler_padd, nblk(s->nc), 256, s->geo, s->PP, s->p[L_IC]);
+}
+static int solve_pressure(hg_state* s, bool second = false) {
   const hg_config& c = s->cfg;
   int it = 0; double df = 0.;
   if (c.linear_solver_pressure == HG_LS_GAUSS_SEIDEL) {
@@ -647,7 +651,7 @@ static int solve_pressure(hg_state* s) {
     double* defer_out = (s->defer && s->world == 1 && s->nsolves < 4096) ? s->sorres + 2 * s->nsolves : nullptr;
     if (int rc = run_sor(s, s->PP, s->nsh, c.lu_relaxed_tolerance, c.lu_relaxed_num_iters_limit, launch, &it, &df, defer_out)) return rc;
     if (!s->defer && s->gs_tiled) if (int rc = gt_check(s)) return rc;   // inside hg_step: part of the step's status block
-    launch_pcorr(s);
+    if (second) launch_padd(s); else launch_pcorr(s);
   } else if (c.linear_solver_pressure == HG_LS_JACOBI) {
     // natural layout: constants back from the sheared array, rows regenerated from d_c
     DIMSEL(s, k_from_sheared, nblk(s->nc), 256, s->geo, s->RP, s->w1);
@@ -655,7 +659,7 @@ static int solve_pressure(hg_state* s) {
                             c.lu_relaxed_relaxation_factor, &it, &df)) return rc;
     // p_curr = p_prev + alpha p'
     DIMSEL(s, k_to_sheared, nblk(s->nc), 256, s->geo, s->pc, s->PP);
-    launch_pcorr(s);
+    if (second) launch_padd(s); else launch_pcorr(s);
   } else if (c.linear_solver_pressure == HG_LS_LU_RELAXED) {
     P7 rows;
     if (s->dim == 3) {
@@ -668,7 +672,7 @@ static int solve_pressure(hg_state* s) {
     }
     if (int rc = run_lu_relaxed(s, s->RP, s->PP, s->X[0], s->X[1], c.lu_relaxed_tolerance, c.lu_relaxed_num_iters_limit,
                                 c.lu_relaxed_relaxation_factor, &it, &df)) return rc;
-    launch_pcorr(s);
+    if (second) launch_padd(s); else launch_pcorr(s);
   } else {   // lu: one forward + backward sweep over the explicit rows (linear.hpp:533-566); the factory reports no sweeps
     P7 rows;
     if (s->dim == 3) {
@@ -680,7 +684,7 @@ static int solve_pressure(hg_state* s) {
       DIMSEL(s, k_prows, nblk(s->nc), 256, s->geo, s->dc, 1, rows);
     }
     if (int rc = solve_system(s, HG_LS_LU, s->RP, s->PP, nullptr, nullptr, &it, &df)) return rc;
-    launch_pcorr(s);
+    if (second) launch_padd(s); else launch_pcorr(s);
   }
   if (!s->defer && s->lu_tiled) if (int rc = lt_check(s)) return rc;   // the momentum solve's dataflow kernel
   if (it < 0) ++s->nsolves;   // deferred: counted on the device, added at the end of the step
@@ -1161,6 +1165,20 @@ extern "C" int hg_fluid_make_iteration(hg_handle s) {   // fluid.hpp:814-1158
     else { k_resid<2><<<gb, 256, 0, s->st>>>(cp3(s->u[L_IC]), cp3(s->u[L_IP]), s->nc, rdst); }
     ++s->launches;
   }
+  if (c.simpler) {   // SIMPLER (fluid.hpp:1060-1155): pressure from the momentum equations evaluated on the new velocity
+    tpush(s, "fluid.8.simpler");
+    SimplerArgs a;
+    for (int t = 0; t < 7; ++t) a.A[t] = s->A[t];
+    for (int n = 0; n < 3; ++n) { a.R[n] = s->R[n]; a.uc[n] = s->u[L_IC][n] ? s->u[L_IC][n] : s->zero; a.up[n] = s->u[L_IP][n] ? s->u[L_IP][n] : s->zero;
+                                  a.fcr[n] = s->fcr[n]; a.gp[n] = s->gp[n]; a.force[n] = s->force[n]; a.fev[n] = s->G[n]; }
+    a.dc = s->dc; a.F = s->F[L_IC]; a.p = s->p[L_IC]; a.rc = c.rhie_chow_factor;
+    a.RP = s->RP; a.CO = s->CO; a.out_mode = s->gs_tiled ? 2 : 1;
+    a.co5.plane = s->co5.plane; a.co5.nxp = s->co5.nxp; a.co5.pad = GT_PAD;
+    DIMSEL(s, k_simpler_eval, gb, 256, s->geo, a);
+    DIMSEL(s, k_simpler_rhs, gb, 256, s->geo, a);
+    if (int rc = solve_pressure(s, true)) return rc;
+    tpop(s);
+  }
   ++s->iter_count;
   s->last_resid = -1.;   // not fetched yet
   return 0;
@@ -1476,7 +1494,8 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
   if ((cfg->dim != 2 && cfg->dim != 3) || cfg->Nx < 1 || cfg->Ny < 1 || (cfg->dim == 3 && cfg->Nz < 1))
     return fail_create(nullptr, HG_ERR_INVALID, "bad mesh size / dim");
   if (cfg->num_phases < 1 || cfg->num_phases > HG_MAX_PHASES) return fail_create(nullptr, HG_ERR_INVALID, "num_phases must be 1..3");
-  if (cfg->simpler) return fail_create(nullptr, HG_ERR_INVALID, "simpler 1 is not on the GPU path");
+  if (cfg->simpler && (cfg->world_size > 1 || (cfg->linear_solver_pressure != HG_LS_GAUSS_SEIDEL && cfg->linear_solver_pressure != HG_LS_JACOBI)))
+    return fail_create(nullptr, HG_ERR_INVALID, "simpler 1 runs on one GPU with gauss_seidel or jacobi for the pressure system");
   if (cfg->velocity_is_carrier) return fail_create(nullptr, HG_ERR_INVALID, "velocity_is_carrier 1 is not on the GPU path");
   for (int ph = 0; ph < cfg->num_phases; ++ph)
     if (cfg->enable_settling[ph] && cfg->world_size > 1) return fail_create(nullptr, HG_ERR_INVALID, "multi-GPU slabs: phase slip is not decomposed");

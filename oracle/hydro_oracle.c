@@ -13,8 +13,8 @@
  * tables computed from node coordinates (mesh3d.hpp:264-460); the two agree to
  * rounding, and exactly when N is a power of two on a unit box.
  *
- * Not restated (the product rejects the same options): SIMPLER (fluid.hpp:1060-1155), geometric force averaging,
- * phase slip/settling, chemistry/radiation, compressibility, PIC advection.
+ * Not restated (the product rejects the same options): geometric force averaging, the carrier-velocity variant of the
+ * phase slip, chemistry/radiation, compressibility, PIC advection, periodic meshes.
  */
 #include "hydro_oracle.h"
 
@@ -38,6 +38,8 @@ struct ho_state {
   signed char* fside;     /* boundary faces: index into bcvel (0..5 sides, 6 box) */
   unsigned char* ftdir;   /* temperature: 1 = Dirichlet (heat box) */
   double bcvel[7][3];
+  double* ma[3][7]; double* mr[3];  /* momentum equations of the iteration (GetVelocityEquations), kept for SIMPLER */
+  double* fev[3];                   /* fc_evaluated */
   double* slipv[HG_MAX_PHASES][3]; /* v_fc_velocity_slip */
   double* fslip[HG_MAX_PHASES];    /* v_ff_volume_flux_slip */
   int any_slip;
@@ -435,6 +437,10 @@ static void convdiff_iteration(struct ho_state* s, double* fl[4], int kind, int 
       coeffsum[c] = cs;
     }
   }
+  if (kind == K_VEL && s->cfg.simpler) {   /* the equations stay available (GetVelocityEquations, conv_diff.hpp) */
+    for (int t = 0; t < 7; ++t) memcpy(s->ma[comp][t], s->a[t], s->nc * sizeof(double));
+    memcpy(s->mr[comp], s->rhs, s->nc * sizeof(double));
+  }
   int it; double df;
   solve(s, solver, s->a, s->rhs, s->corr, &it, &df);                 /* :245 */
   for (size_t c = 0; c < s->nc; ++c) curr[c] = prev[c] + s->corr[c]; /* :246-248 */
@@ -648,6 +654,59 @@ int ho_fluid_make_iteration(ho_handle s) {                           /* fluid.hp
       }
       s->F[L_IC][f] = r;
     }
+  }
+  if (cfg->simpler) {                                                /* fluid.hpp:1060-1155 */
+    long off[7]; nb_offsets(s, off);
+    for (int d = 0; d < dim; ++d) interp(s, s->u[L_IC][d], K_VEL, d, s->ffu[d]);   /* ff_velocity :1069-1071 */
+    /* fc_evaluated = momentum equations on the velocity change + restored force - pressure gradient :1073-1094 */
+    for (int k = 0; k < s->n[2]; ++k) for (int j = 0; j < s->n[1]; ++j) for (int i = 0; i < s->n[0]; ++i) {
+      size_t c = cidx(s, i, j, k);
+      for (int n = 0; n < dim; ++n) {
+        double ev = s->mr[n][c];
+        for (int t = 0; t < 7; ++t) {
+          if (t != CD && !(nb_exists(s, i, j, k, t) && s->ma[n][t][c] != 0.)) continue;   /* terms of the expression only */
+          long nb = (long)c + off[t];
+          ev += (s->u[L_IC][n][nb] - s->u[L_IP][n][nb]) * s->ma[n][t][c];
+        }
+        s->fev[n][c] = ev + (s->fcr[n][c] - s->gp[n][c]);
+      }
+    }
+    for (int d = 0; d < dim; ++d) interp(s, s->fev[d], K_NONE, 0, s->wf3[d]);     /* ff_evaluated :1096-1097 */
+    /* ff_rhs :1099-1112 -> kf */
+    double* frhs = s->kf;
+    memset(frhs, 0, s->nf * sizeof(double));
+    for (int d = 0; d < dim; ++d) {
+      int ex = s->n[0] + (d == 0), ey = s->n[1] + (d == 1), ez = s->n[2] + (d == 2);
+      for (int k = 0; k < ez; ++k) for (int j = 0; j < ey; ++j) for (int i = 0; i < ex; ++i) {
+        size_t f = fidx(s, d, i, j, k);
+        if (s->ftype[f] != FT_INNER) continue;
+        double dot1 = 0., dot2 = 0.;
+        for (int c = 0; c < dim; ++c) {
+          const double S = (c == d ? s->area[d] : 0.);
+          dot1 += (s->wf3[c][f] - s->ffe[c][f]) * S;
+          dot2 += s->ffu[c][f] * S;
+        }
+        frhs[f] = dot1 / s->dfc[f] + (s->F[L_IC][f] - dot2) / cfg->rhie_chow_factor;
+      }
+    }
+    /* constants :1114-1121, cell conditions :1124-1141 (the terms towards the fixed cell were removed by the first
+     * solve's SetKnownValue), then constant := Evaluate(pressure) :1143-1146 */
+    for (int k = 0; k < s->n[2]; ++k) for (int j = 0; j < s->n[1]; ++j) for (int i = 0; i < s->n[0]; ++i) {
+      size_t c = cidx(s, i, j, k);
+      double sum = 0.;
+      for (int q = 0; q < 2 * dim; ++q) sum += frhs[nface(s, i, j, k, q)] * ((q & 1) ? 1. : -1.);
+      double cst = -sum;
+      if ((long)c == s->pfix_cell) cst = -cfg->pressure_fixed_value;
+      for (int t = 0; t < 7; ++t) {
+        if (t != CD && !(nb_exists(s, i, j, k, t) && s->a[t][c] != 0.)) continue;
+        cst += pcurr[(long)c + off[t]] * s->a[t][c];
+      }
+      s->rhs[c] = cst;
+    }
+    int it2; double df2;
+    solve(s, cfg->linear_solver_pressure, s->a, s->rhs, s->pc, &it2, &df2);    /* :1148 */
+    s->last_sweeps_total += it2 + 1; s->last_diff = df2;
+    for (size_t c = 0; c < s->nc; ++c) pcurr[c] += s->pc[c];                   /* :1150-1152 */
   }
   ++s->iter_count;
   return 0;
@@ -997,7 +1056,7 @@ static int inside(const double lb[3], const double rt[3], const double x[3], int
 int ho_create(const hg_config* cfg, ho_handle* out) {
   if (!cfg || !out) return HG_ERR_INVALID;
   if ((cfg->dim != 2 && cfg->dim != 3) || cfg->num_phases < 1 || cfg->num_phases > HG_MAX_PHASES ||
-      cfg->simpler || cfg->force_geometric_average || cfg->velocity_is_carrier) {
+      cfg->force_geometric_average || cfg->velocity_is_carrier) {
     snprintf(g_err, sizeof g_err, "unsupported configuration"); return HG_ERR_INVALID;
   }
   struct ho_state* s = (struct ho_state*)calloc(1, sizeof *s);
@@ -1066,6 +1125,7 @@ int ho_create(const hg_config* cfg, ho_handle* out) {
   }
   for (int ph = 0; ph < HG_MAX_PHASES; ++ph) { s->vf[ph] = dalloc(nc); s->pd_inlet[ph] = dalloc(nf); }
   for (int d = 0; d < 3; ++d) s->outvel[d] = dalloc(nf);
+  if (cfg->simpler) for (int n = 0; n < 3; ++n) { s->mr[n] = dalloc(nc); s->fev[n] = dalloc(nc); for (int t = 0; t < 7; ++t) s->ma[n][t] = dalloc(nc); }
   for (int ph = 0; ph < HG_MAX_PHASES; ++ph) { s->fslip[ph] = dalloc(nf); for (int d = 0; d < 3; ++d) s->slipv[ph][d] = dalloc(nc); if (ph < cfg->num_phases && cfg->enable_settling[ph]) s->any_slip = 1; }
   for (int sd = 0; sd < 2 * dim; ++sd) if (cfg->condition_kind[sd] == HG_BC_OUTLET) s->any_outlet = 1;
   s->rho_raw = dalloc(nc); s->rho = dalloc(nc); s->mu = dalloc(nc); s->kc = dalloc(nc);
@@ -1151,6 +1211,7 @@ int ho_destroy(ho_handle s) {
   }
   for (int ph = 0; ph < HG_MAX_PHASES; ++ph) { free(s->vf[ph]); free(s->pd_inlet[ph]); }
   for (int d = 0; d < 3; ++d) free(s->outvel[d]);
+  for (int n = 0; n < 3; ++n) { free(s->mr[n]); free(s->fev[n]); for (int t = 0; t < 7; ++t) free(s->ma[n][t]); }
   for (int ph = 0; ph < HG_MAX_PHASES; ++ph) { free(s->fslip[ph]); for (int d = 0; d < 3; ++d) free(s->slipv[ph][d]); }
   free(s->rho_raw); free(s->rho); free(s->mu); free(s->kc); free(s->qvol); free(s->qmass); free(s->tsrc);
   free(s->muf); free(s->ffp); free(s->dc); free(s->dfc); free(s->Fs); free(s->cf);

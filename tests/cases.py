@@ -107,6 +107,9 @@ GOLDEN_CASES = {
     "rt3d_8_settling": (rt3d(8, enable_settling_1=1, bubble_radius_1=0.02, initial_volume_fraction_smooth_times=2), 3),
     "dam2d_32x16_settling": (broken_dam_2d(32, 16, enable_settling_0=1, bubble_radius_0=0.0004, enable_settling_1=1,
                                            bubble_radius_1=0.0002, lu_relaxed_num_iters_limit=40), 3),
+    # SIMPLER: second pressure solve per iteration (fluid.hpp:1060-1155)
+    "rt3d_8_simpler": (rt3d(8, simpler=1), 2),
+    "cavity_16_simpler": (cavity(16, simpler=1, num_iterations_limit=5, lu_relaxed_num_iters_limit=30), 3),
     "thermal2d_24x12_vellur_heatgs": (thermal_2d(24, 12, linear_solver_velocity="lu_relaxed", linear_solver_heat="gauss_seidel",
                                                  lu_relaxed_num_iters_limit=12, lu_relaxed_relaxation_factor=0.7), 2),
 }

@@ -110,7 +110,7 @@ def test_gpu_matches_oracle_and_reference_fixture(name):
 @pytest.mark.parametrize("name", ["rt3d_16", "dam3d_32x10x10", "thermal2d_32x16", "cavity_16", "rt3d_8_jacobi_dtauto",
                                   "dam2d_36x20", "rt3d_12x10x9", "cavity_12_lurelaxed", "cavity_12_velgs_plu", "rt3d_8_veljacobi",
                                   "thermal2d_24x12_vellur_heatgs", "rt3d_8_sharp_split", "dam2d_32x16_sharp", "channel2d_32x16_outlet",
-                                  "rt3d_8_inlet_outlet", "rt3d_8_settling", "dam2d_32x16_settling"])
+                                  "rt3d_8_inlet_outlet", "rt3d_8_settling", "dam2d_32x16_settling", "rt3d_8_simpler", "cavity_16_simpler"])
 def test_gpu_bit_exact_from_identical_state(name):
     """Started from bit-identical fields (the oracle's initial state uploaded through hg_set_field, which
     removes the 1-ulp difference between device and host sin() in the initial velocity), the CUDA path
@@ -355,7 +355,7 @@ def test_error_convention():
     """Unsupported options fail in hg_create with a message instead of silently falling back."""
     from hydro_b200.capi import Hydro
     with pytest.raises(RuntimeError, match="simpler"):
-        Hydro(cases.cavity(8, simpler=1))
+        Hydro(cases.cavity(8, simpler=1, linear_solver_pressure="lu_relaxed"))
     with pytest.raises(RuntimeError, match="outlet"):
         Hydro(cases.rt3d(8, condition_right="outlet"), world_size=2, rank=0)
     with pytest.raises(RuntimeError, match="slabs support lu"):
