@@ -45,8 +45,9 @@ constexpr int LT_PBIAS = 1;
 constexpr int LT_CTAS_PER_SM = LT_CTAS_N;
 // ring of operand slots in (dynamic) shared memory: [LT_PF][7 arrays][LT_WORK] doubles, filled by cp.async
 constexpr int LT_RING_BYTES = LT_PF * 7 * LT_TX * LT_TY_N * 8;
-DV void lt_cp_async8(unsigned dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src) : "memory");
+// 8-byte copy global -> shared; bytes = 0: nothing is read (the destination is zero-filled)
+DV void lt_cp_async8(unsigned dst, const void* src, unsigned bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(dst), "l"(src), "r"(bytes) : "memory");
 }
 DV void lt_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> DV void lt_cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
@@ -62,7 +63,15 @@ struct LtArgs {
   int* ctl;             // [0] next box, [1] abort flag
   SlabLink link;        // z-slab decomposition: tagged interface planes of the neighbouring slabs (hg_slab.cuh); component n at + n link_stride
   long long link_stride;
+#ifdef LT_TRACE
+  unsigned long long* trace;   // diagnostics build: per box (claimed, first macro step started, finished) in ns + SM id
+  unsigned long long* trace2;  // [box][4][128]: per macro step: workers started it / published / halo warp's poll succeeded / stage stored
+#endif
 };
+#ifdef LT_TRACE
+DV unsigned long long lt_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+DV unsigned lt_smid() { unsigned r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
+#endif
 
 DV int lt_ld_acquire(const int* p) {
   int v;
@@ -126,6 +135,9 @@ __global__ void __launch_bounds__(LT_THREADS, LT_CTAS_PER_SM) k_lu_tiled(Geo g, 
     const int nmacro = (Shi - Slo + LT_M) / LT_M;
     const int me = bx.y * a.nbi + bx.x;
     const int dep_x = bx.x > 0 ? me - 1 : -1, dep_y = bx.y > 0 ? me - a.nbi : -1;
+#ifdef LT_TRACE
+    if (tid == 0 && a.trace) { a.trace[me * 4] = lt_now(); a.trace[me * 4 + 3] = lt_smid(); }
+#endif
     for (int q = tid; q < 2 * 3 * LT_FRAME; q += LT_THREADS) (&fr[0][0][0])[q] = 0.;
     for (int q = tid; q < 2 * LT_M * 3 * LT_HALO; q += LT_THREADS) (&stage[0][0][0][0])[q] = 0.;
     if (tid == 0) s_prog = 0;
@@ -136,7 +148,11 @@ __global__ void __launch_bounds__(LT_THREADS, LT_CTAS_PER_SM) k_lu_tiled(Geo g, 
         int last = 0;
         for (;;) {
           const int v = lt_ld_acquire_cta(&s_prog);
-          if (v != last) { lt_st_release(&a.progress[me], v); last = v; if (v == 0x7fffffff) break; }
+          if (v != last) { lt_st_release(&a.progress[me], v); last = v; if (v == 0x7fffffff) break;
+#ifdef LT_TRACE
+                           { const int mm = (v - LT_PBIAS - Slo) / LT_M; if (a.trace2 && mm >= 0 && mm < 128) a.trace2[((long long)me * 4 + 1) * 128 + mm] = lt_now(); }
+#endif
+          }
           else { if (LT_SLEEP_NS > 0) __nanosleep(LT_SLEEP_NS); }
         }
       }
@@ -167,6 +183,9 @@ __global__ void __launch_bounds__(LT_THREADS, LT_CTAS_PER_SM) k_lu_tiled(Geo g, 
             }
           }
           __syncwarp();
+#ifdef LT_TRACE
+          if (lane == 0 && a.trace2 && m < 128) a.trace2[((long long)me * 4 + 2) * 128 + m] = lt_now();
+#endif
           // entry e of a frame's halo: e < TY: column 0, row e+1 (x-neighbour of thread (0, e)); else row 0, column e-TY+1
           double hvv[NE][3]; bool hok[NE];
 #pragma unroll
@@ -182,8 +201,9 @@ __global__ void __launch_bounds__(LT_THREADS, LT_CTAS_PER_SM) k_lu_tiled(Geo g, 
             long long c = (DIR ? ((long long)(g.np - S) * ny + qj) * nx + qi : ((long long)(S + 1) * ny + qj) * nx + qi) - (isx ? nbx : nby);
             if (!v) c = 0;
             hok[r] = v;
+            // (entries without a cell are not loaded: every box asking for the same spare entry would make it a hot spot in L2)
 #pragma unroll
-            for (int n = 0; n < 3; ++n) hvv[r][n] = __ldcg(&dstx[n][c]);
+            for (int n = 0; n < 3; ++n) hvv[r][n] = v ? __ldcg(&dstx[n][c]) : 0.;
           }
 #pragma unroll
           for (int r = 0; r < NE; ++r) {
@@ -194,6 +214,9 @@ __global__ void __launch_bounds__(LT_THREADS, LT_CTAS_PER_SM) k_lu_tiled(Geo g, 
               for (int n = 0; n < 3; ++n) stage[m & 1][st][n][e] = hok[r] ? hvv[r][n] : 0.;
             }
           }
+#ifdef LT_TRACE
+          if (lane == 0 && a.trace2 && m < 128) a.trace2[((long long)me * 4 + 3) * 128 + m] = lt_now();
+#endif
         }
         lt_bar_macro();
       }
@@ -213,17 +236,21 @@ __global__ void __launch_bounds__(LT_THREADS, LT_CTAS_PER_SM) k_lu_tiled(Geo g, 
     // into the thread's own entries of a ring in shared memory: the rows come from DRAM (the sheared arrays are written
     // once and read once), and a step is much shorter than a DRAM round trip -- round 1 kept them in registers 4 steps
     // ahead and every step waited for memory.  Threads without a cell at that step read entry 0 of the arrays (an unused
-    // corner entry) and their result is discarded: unconditional copies, issued back to back.
+    // corner entry) with a source size of zero -- nothing is read, the entry is zero-filled, the result is discarded:
+    // unconditional copies, issued back to back.  (Reading the corner entry for real made it a hot spot: while a box fills or
+    // drains most of its threads have no cell, and every warp of every box asked L2 for the same seven sectors in every step --
+    // the first steps of a box ran at half speed, which is what a dependent box waits for.)
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(lt_ring) + tid * 8;
     auto request_ops = [&](int slot, long long c, int S) {
       const int kp = S - ip - jp;
       const bool v = col && kp >= 0 && kp < nz;
       if (!v) c = 0;
+      const unsigned nb = v ? 8u : 0u;
       const unsigned d = ring_s + slot * (7 * LT_WORK * 8);
-      lt_cp_async8(d, Az + c); lt_cp_async8(d + LT_WORK * 8, Ay + c); lt_cp_async8(d + 2 * LT_WORK * 8, Ax + c);
-      lt_cp_async8(d + 3 * LT_WORK * 8, Ad + c);
+      lt_cp_async8(d, Az + c, nb); lt_cp_async8(d + LT_WORK * 8, Ay + c, nb); lt_cp_async8(d + 2 * LT_WORK * 8, Ax + c, nb);
+      lt_cp_async8(d + 3 * LT_WORK * 8, Ad + c, nb);
 #pragma unroll
-      for (int n = 0; n < 3; ++n) lt_cp_async8(d + (4 + n) * LT_WORK * 8, src[n] + c);
+      for (int n = 0; n < 3; ++n) lt_cp_async8(d + (4 + n) * LT_WORK * 8, src[n] + c, nb);
       lt_cp_commit();
     };
 #pragma unroll 1
@@ -233,6 +260,10 @@ __global__ void __launch_bounds__(LT_THREADS, LT_CTAS_PER_SM) k_lu_tiled(Geo g, 
     for (int m = 0; m < nmacro; ++m) {
       const int S0 = Slo + m * LT_M;
       lt_bar_macro();   // macro step m-1 is complete; the stage of macro step m is loaded
+#ifdef LT_TRACE
+      if (tid == 0 && m == 0 && a.trace) a.trace[me * 4 + 1] = lt_now();
+      if (tid == 0 && a.trace2 && m < 128) a.trace2[((long long)me * 4 + 0) * 128 + m] = lt_now();
+#endif
       if (tid == 0 && m > 0) lt_st_release_cta(&s_prog, S0 + LT_PBIAS);   // steps < S0 are complete (publisher warp)
       // ---- LT_M steps
 #pragma unroll
@@ -290,6 +321,9 @@ __global__ void __launch_bounds__(LT_THREADS, LT_CTAS_PER_SM) k_lu_tiled(Geo g, 
       }
     }
     lt_bar_macro();   // all steps done (the halo warp takes part)
+#ifdef LT_TRACE
+    if (tid == 0 && a.trace) a.trace[me * 4 + 2] = lt_now();
+#endif
     if (tid == 0) lt_st_release_cta(&s_prog, 0x7fffffff);
   }
 }

@@ -713,6 +713,14 @@ static int solve_lu_tiled(hg_state* s, int ncomp, double* const* Rs = nullptr, d
   if (s->profile_on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s->st); }
   int grid = std::min(s->lt_nboxes, s->num_sms * LT_CTAS_PER_SM);   // all boxes resident when they fit
   if (s->cfg.solver_ctas > 0) grid = std::min(grid, s->cfg.solver_ctas);           // ranks sharing a device (tests)
+#ifdef LT_TRACE
+  static unsigned long long* trace_dev = nullptr; static int trace_calls = 0;
+  if (!trace_dev) cudaMalloc((void**)&trace_dev, (size_t)s->lt_nboxes * 4 * sizeof(unsigned long long));
+  a.trace = trace_dev;
+  static unsigned long long* trace2_dev = nullptr;
+  if (!trace2_dev) { cudaMalloc((void**)&trace2_dev, (size_t)s->lt_nboxes * 512 * 8); cudaMemset(trace2_dev, 0, (size_t)s->lt_nboxes * 512 * 8); }
+  a.trace2 = trace2_dev;
+#endif
   for (int dir = 0; dir < 2; ++dir) {
     CK(cudaMemsetAsync(s->lt_progress, 0, s->lt_nboxes * sizeof(int), s->st));
     CK(cudaMemsetAsync(s->lt_ctl, 0, sizeof(int), s->st));   // next-box counter; the abort flag [1] is sticky
@@ -725,6 +733,23 @@ static int solve_lu_tiled(hg_state* s, int ncomp, double* const* Rs = nullptr, d
     }
     CK(cudaGetLastError());
     ++s->launches;
+#ifdef LT_TRACE
+    if (getenv("HYDRO_LT_TRACE") && ++trace_calls == 25 + dir) {   // one forward and one backward launch of a warmed-up step
+      CK(cudaStreamSynchronize(s->st));
+      std::vector<unsigned long long> h((size_t)s->lt_nboxes * 4);
+      cudaMemcpy(h.data(), trace_dev, h.size() * 8, cudaMemcpyDeviceToHost);
+      FILE* f = fopen((std::string(getenv("HYDRO_LT_TRACE")) + (dir ? ".bwd" : ".fwd")).c_str(), "w");
+      if (f) { fprintf(f, "%d %d\n", s->lt_nboxes, s->lt_nbi);
+               for (int q = 0; q < s->lt_nboxes; ++q) fprintf(f, "%d %llu %llu %llu %llu\n", q, h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+               fclose(f); }
+      if (dir == 0) {
+        std::vector<unsigned long long> h2((size_t)s->lt_nboxes * 512);
+        cudaMemcpy(h2.data(), trace2_dev, h2.size() * 8, cudaMemcpyDeviceToHost);
+        FILE* f2 = fopen((std::string(getenv("HYDRO_LT_TRACE")) + ".macro").c_str(), "wb");
+        if (f2) { fwrite(h2.data(), 8, h2.size(), f2); fclose(f2); }
+      }
+    }
+#endif
   }
   if (e0) { cudaEventRecord(e1, s->st); s->prof_ev[1].push_back({e0, e1}); }
   return 0;
