@@ -1587,7 +1587,7 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
   g.excl = nullptr;
 
   // ---- allocation: cell arrays carry HG_HALO planes on both sides (pointer = first owned cell)
-  const long long nc = s->nc, nf = s->nf;
+  const long long nf = s->nf;
   {
     bool okA = true;
     const long long ncell = s->nxy * (s->n[2] + 2 * HG_HALO);
