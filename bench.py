@@ -373,10 +373,15 @@ def run_b200(args, rank, local_rank, world):
         ha = Hydro(workload_params(n, "rt", as_configured=True), device=local_rank)
         ha.step()
         ha.synchronize()
+        ha.profile_enable(True)
+        ha.profile_read(0), ha.profile_read(1)
         ha.event_record(0)
-        sts = [ha.step() for _ in range(2)]
+        sts = [ha.step() for _ in range(5)]
         ha.event_record(1)
         ha.synchronize()
+        a_gs_n, a_gs_ms = ha.profile_read(0)
+        a_lu_n, a_lu_ms = ha.profile_read(1)
+        ha.profile_enable(False)
         ams = ha.event_elapsed_ms(0, 1) / len(sts)
         sim = sum(s_.simple_iterations for s_ in sts) / len(sts)
         swp = sum(s_.pressure_sweeps_total for s_ in sts) / len(sts)
@@ -384,6 +389,10 @@ def run_b200(args, rank, local_rank, world):
         asconf = {"workload": "RT-3D %d^3 as configured: <= 20 SIMPLE iterations (tol 1e-4), gauss_seidel <= 1000 sweeps (tol 1e-5)" % n,
                   "ms_per_step": ams, "value": cells / (ams * 1e-3), "unit": UNIT, "steps": len(sts),
                   "simple_iterations_per_step": sim, "pressure_sweeps_per_step": swp,
+                  # sweep launches incl. the replayed chunks: (kernel time) / (sweeps the reference executes x time per sweep
+                  # of the fixed-work launch) is the price of finding the stopping sweep after the fact
+                  "sweep_launches_per_step": a_gs_n / len(sts), "sweep_kernel_ms_per_step": a_gs_ms / len(sts),
+                  "lu_ms_per_step": a_lu_ms / len(sts),
                   "algorithmic_bytes_per_cell_step": bp, "frac_of_peak": bp * cells / (ams * 1e-3) / 1e9 / measured_peak()[0]}
         ha.close()
     if rank != 0:

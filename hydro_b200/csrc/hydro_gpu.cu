@@ -62,6 +62,7 @@ struct hg_state {
   int gt_plan_cap = 0; long long gt_plan_clock = 0;
   int* gt_ctl = nullptr;
   std::vector<int> sor_pred = std::vector<int>(256, -1);   // stopping sweep of the pressure solve of SIMPLE iteration q in the previous step
+  std::vector<int> sor_old = std::vector<int>(256, -1);    // ... and in the step before that (trend of the prediction)
   int gt_gbase = 0;                           // sweep groups of the current solve launched so far (parity of the slabs' "down" planes)
   unsigned long long* gt_clk = nullptr;
   // lu as a dataflow of column boxes (hg_lu_tiled.cuh)
@@ -383,20 +384,34 @@ static int run_sor(hg_state* s, double* x, long long nx_, double tol, int limit,
   int chunk = s->cfg.pressure_sweeps_per_check > 0 ? s->cfg.pressure_sweeps_per_check : 128;
   if (chunk > SOLVER_SC) chunk = SOLVER_SC;
   // The stopping sweep is only known after the fact, and a chunk that runs past it is replayed from its checkpoint with the
-  // exact count: a fixed chunk of 128 sweeps executes up to twice the sweeps the reference does.  The stopping sweep of the
-  // same SIMPLE iteration of the previous time step is a good predictor (the system changes slowly): the first chunk ends a
-  // few sweeps before it, then short chunks (doubling) follow -- the replay costs a few sweeps.  Without a prediction: `chunk`.
+  // exact count: fixed chunks of 128 sweeps execute up to twice the sweeps the reference does.  Prediction: the stopping sweep of
+  // the same SIMPLE iteration of the previous time step, scaled by the trend seen since (iteration q-1 of this step against
+  // iteration q-1 of the previous step; for the first iteration the previous step against the one before) -- during the start-up
+  // of a flow the counts fall by a third from step to step, and a prediction that is too high costs a whole chunk (the stop lies
+  // inside it: replay), one that is too low only a few short chunks.  So phase 1 runs to a fraction of the prediction in chunks of
+  // up to `chunk` sweeps, phase 2 continues in short chunks of constant size.  Without a prediction: `chunk`.
   const int pidx = std::min(std::max(s->iter_count, 0), (int)s->sor_pred.size() - 1);
   const int pred = s->sor_pred[pidx];
-  int small = 8;
-  int done = 0;
-  while (done < max_total) {
-    int n = chunk;
-    if (pred >= 0) {
-      if (done == 0 && pred + 1 - 4 >= small) n = std::min(chunk, pred + 1 - 4);
-      else { n = std::min(chunk, small); small *= 2; }
+  static const int margin = getenv("HYDRO_SOR_MARGIN") ? std::max(0, atoi(getenv("HYDRO_SOR_MARGIN"))) : 4;
+  static const int small = getenv("HYDRO_SOR_SMALL") ? std::max(1, atoi(getenv("HYDRO_SOR_SMALL"))) : 16;
+  static const double frac = getenv("HYDRO_SOR_FRAC") ? atof(getenv("HYDRO_SOR_FRAC")) : 0.7;
+  static const int probe = getenv("HYDRO_SOR_PROBE") ? std::max(4, atoi(getenv("HYDRO_SOR_PROBE"))) : 32;
+  static const bool sor_trace = getenv("HYDRO_SOR_TRACE") != nullptr;   // diagnostics: prediction, stopping sweep, sweeps executed
+  // first chunk: a probe of at most 32 sweeps (shorter when the history with its trend says so: the counts can drop abruptly
+  // from one step to the next, and a first chunk that contains the stop is replayed whole); every further chunk from the decay of
+  // the norm inside this solve -- the last 16 sweeps extrapolated to the tolerance, a fraction of it, at least `small` sweeps
+  int n_next = std::min(chunk, probe);
+  if (pred >= 0) {
+    const int tq = pidx > 0 ? pidx - 1 : 0;   // where the trend is read
+    if (s->sor_pred[tq] >= 0 && s->sor_old[tq] > 0) {
+      const double trend = std::min(1.25, std::max(0.25, (double)(s->sor_pred[tq] + 1) / (s->sor_old[tq] + 1)));
+      const int hist = std::max(small, std::max(0, (int)(frac * trend * (pred + 1)) - margin) & ~(GT_B - 1));   // whole sweep groups
+      n_next = std::min(n_next, hist);
     }
-    n = std::min(n, max_total - done);
+  }
+  int done = 0, executed = 0;
+  while (done < max_total) {
+    int n = std::min(std::min(n_next, chunk), max_total - done);
     CK(cudaMemcpyAsync(s->PPsave, x, nx_ * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
     const int gbase_save = s->gt_gbase;
     if (s->world > 1) {
@@ -404,6 +419,7 @@ static int run_sor(hg_state* s, double* x, long long nx_, double tol, int limit,
       CK(cudaMemcpyAsync(s->slab.ll + SLAB_LL_DOWN_SAVE * s->nxy, s->slab.ll + SLAB_LL_DOWN * s->nxy, 2LL * SLAB_GB * s->nxy * sizeof(uint4), cudaMemcpyDeviceToDevice, s->st));
     }
     if (int rc = launch(done, done + n)) return rc;
+    executed += n;
     if (int rc = slab_reduce(s, s->diffs + done, n, 0, s->hdiffs + done)) return rc;
     int stop = -1;
     for (int k = done; k < done + n; ++k) if (!(s->hdiffs[k] > tol)) { stop = k; break; }
@@ -418,15 +434,24 @@ static int run_sor(hg_state* s, double* x, long long nx_, double tol, int limit,
         CK(cudaMemsetAsync(s->diffs + done, 0, n * sizeof(double), s->st));
         if (int rc = slab_sync(s)) return rc;
         if (int rc = launch(done, stop + 1)) return rc;
+        executed += stop + 1 - done;
       }
+      if (sor_trace) fprintf(stderr, "sor: iteration %d predicted %d stopped at %d, %d sweeps executed for %d\n", s->iter_count, pred, stop, executed, stop + 1);
       *out_iter = stop; *out_diff = s->hdiffs[stop];
-      s->sor_pred[pidx] = stop;
+      s->sor_old[pidx] = s->sor_pred[pidx]; s->sor_pred[pidx] = stop;
       return 0;
     }
     done += n;
+    n_next = small;
+    { const int k1 = done - 1, k0 = std::max(0, k1 - 16);
+      const double d1 = s->hdiffs[k1], d0 = s->hdiffs[k0];
+      if (k1 > k0 && d1 > tol && d0 > d1) {
+        const double rem = std::log(tol / d1) / (std::log(d1 / d0) / (k1 - k0));   // sweeps still to go at this decay
+        if (rem > 0. && rem < 1e6) n_next = std::max(small, (int)(frac * rem) & ~(GT_B - 1));
+      } }
   }
   *out_iter = limit + 1; *out_diff = s->hdiffs[max_total - 1];
-  s->sor_pred[pidx] = max_total - 1;
+  s->sor_old[pidx] = s->sor_pred[pidx]; s->sor_pred[pidx] = max_total - 1;
   return 0;
 }
 
