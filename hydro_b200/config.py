@@ -416,6 +416,18 @@ class Params(dict):
     # -- .hydroconf text -----------------------------------------------------
     _set_re = re.compile(r"^\s*set\s+(\w+)\s+(\w+)\s+(.*?)\s*$")
 
+    @staticmethod
+    def _as_console_text(v):
+        """A parameter value as `$(name)` substitutes it: written with the stream's default formatting (6 significant digits,
+        `2.0` -> `2`) and read back as one token (console.cpp:464-509), so `$(T)0` with T = 2 is `20`."""
+        if isinstance(v, bool):
+            return "1" if v else "0"
+        if isinstance(v, float):
+            return "%g" % v
+        if isinstance(v, (tuple, list)):
+            return "(" + ",".join("%g" % x for x in v) + ")"
+        return str(v).split()[0] if str(v).split() else ""
+
     def read_hydroconf(self, text):
         """Apply `set <type> <name> <value>` / `del <name>` lines (console.cpp:276-314)."""
         for raw in text.splitlines():
@@ -429,7 +441,7 @@ class Params(dict):
             if not m:
                 continue  # console commands (ae, run, init, start ...) are the caller's business
             typ, name, val = m.groups()
-            val = re.sub(r"\$\((\w+)\)|\$(\w+)", lambda g: str(self[g.group(1) or g.group(2)]), val)
+            val = re.sub(r"\$\((\w+)\)|\$(\w+)", lambda g: self._as_console_text(self[g.group(1) or g.group(2)]), val)
             if typ in ("int", "c_int"):
                 self[name] = int(val)
             elif typ in ("double", "c_double"):

@@ -72,6 +72,37 @@ def test_params_parse_hydroconf_text():
     assert c.pressure_fixed_enable == 0 and p["max_frame_index"] == 160
 
 
+def test_substitution_prints_values_like_the_console():
+    """`$(name)` substitutes what the console prints for the parameter (console.cpp:464-509: stream default formatting, one
+    token): rt/mfer.hydroconf:51,70 sets `double T 20` and `int max_frame_index $(T)0` = 200."""
+    p = Params()
+    p.read_hydroconf("""
+        set double T 20
+        set int max_frame_index $(T)0
+        set double half 0.5
+        set double dt_out $(half)
+        set int n $T
+    """)
+    assert p["max_frame_index"] == 200 and p["dt_out"] == 0.5 and p["n"] == 20
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/examples"), reason="needs the reference tree (build container)")
+def test_every_example_script_of_the_reference_parses():
+    import glob
+    gen = open("/root/reference/examples/general.hydroconf").read()
+    files = sorted(glob.glob("/root/reference/examples/*/*.hydroconf"))
+    assert len(files) > 40
+    for f in files:
+        p = Params()
+        p.read_hydroconf(gen)
+        p.read_hydroconf(open(f).read())
+    p = Params()
+    p.read_hydroconf(gen)
+    p.read_hydroconf(open("/root/reference/examples/broken_dam_3d/broken_dam_3d.hydroconf").read())
+    c = p.to_struct()
+    assert (c.dim, c.Nx, c.Ny, c.Nz) == (3, 167, 57, 62)
+
+
 def test_missing_parameter_raises_like_reference():
     p = Params()
     del p["Nx"]
