@@ -12,6 +12,7 @@ import re
 HG_MAX_PHASES = 3
 LINEAR_SOLVERS = {"lu": 0, "lu_relaxed": 1, "gauss_seidel": 2, "jacobi": 3}
 BC_KINDS = {"wall": 0, "inlet": 1, "outlet": 2}
+MESHVEL_AUTO = {"vx": 1, "vcx": 2}
 SIDES = ["left", "right", "bottom", "top", "close", "far"]
 
 d3 = C.c_double * 3
@@ -53,7 +54,8 @@ class HgConfig(C.Structure):
         ("world_size", C.c_int), ("rank", C.c_int), ("device", C.c_int),
         ("pressure_sweeps_per_check", C.c_int), ("solver_ctas", C.c_int),
         ("enable_settling", C.c_int * HG_MAX_PHASES), ("velocity_is_carrier", C.c_int), ("bubble_radius", dP),
-        ("reserved", C.c_int * 6),
+        ("meshvel_auto", C.c_int), ("reserved0", C.c_int), ("meshvel_weight", C.c_double),
+        ("reserved", C.c_int * 2),
     ]
 
 
@@ -517,6 +519,14 @@ class Params(dict):
             if v not in LINEAR_SOLVERS:
                 raise ValueError("Unknown linear solver '%s'" % v)
             setattr(c, name, LINEAR_SOLVERS[v])
+        # automatic mesh velocity (hydro2d.hpp:1510-1524): present = on; the reference asserts on any other value
+        if "meshvel_auto" in p:
+            if p["meshvel_auto"] not in MESHVEL_AUTO:
+                raise ValueError("Unknown meshvel_auto=%s" % p["meshvel_auto"])
+            c.meshvel_auto = MESHVEL_AUTO[p["meshvel_auto"]]
+            c.meshvel_weight = float(need("meshvel_weight"))
+        else:
+            c.meshvel_auto, c.meshvel_weight = 0, float(p.get("meshvel_weight", 0.5))
         if need("advection_solver") != "tvd":
             raise ValueError("only advection_solver tvd is on the GPU path")
         c.world_size, c.rank, c.device = world_size, rank, device
@@ -545,7 +555,7 @@ class Params(dict):
 def reject_unsupported(p):
     """Options that change the reference's results but are not on the GPU path fail loudly instead of being
     dropped (hydro2d.hpp:326-368 initial images / deforming velocity, 1030-1122 phase slip, 1129/1387 compressibility,
-    1163-1185 chemistry, 1294 radiation, 1511-1524 automatic mesh velocity)."""
+    1163-1185 chemistry, 1294 radiation)."""
     def truthy(k):
         v = p.get(k, 0)
         return bool(int(v)) if not isinstance(v, str) else v not in ("", "0")
@@ -554,7 +564,7 @@ def reject_unsupported(p):
             raise ValueError("%s 1 is not on the GPU path" % k)
     if str(p.get("chemistry", "steady")) != "steady" or float(p.get("chem_intensity", 0.0)) != 0.0:
         raise ValueError("chemistry other than 'steady' with chem_intensity 0 is not on the GPU path")
-    for k in ("meshvel_auto", "imgu_init", "imgv_init", "img_init"):
+    for k in ("imgu_init", "imgv_init", "img_init"):
         if k in p:
             raise ValueError("%s is not on the GPU path" % k)
     if truthy("velocity_is_carrier"):

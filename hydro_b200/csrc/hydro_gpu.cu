@@ -88,6 +88,7 @@ struct hg_state {
   double* hdiffs = nullptr;   // pinned
   double time_fluid = 0., time_adv = 0., dt = 0., dt_adv = 0.;
   double meshpos[3] = {0., 0., 0.};
+  double stat_cx[HG_MAX_PHASES] = {0., 0., 0.}; bool stat_cx_set[HG_MAX_PHASES] = {false, false, false};   // stat_cx_<i> of the previous CalcStat
   int iter_count = 0;
   double last_resid = 1.;
   int sweeps_total = 0; double last_diff = 0.;
@@ -952,6 +953,18 @@ static int calc_stat_finish(hg_state* s, hg_step_stats* st) {
       o.velocity[p][d] = d < s->dim ? r[4 + d] / r[0] : 0.;
     }
   }
+  // stat_vcx_<i> = (cx - previous cx) / dt, 0 at the first call (hydro2d.hpp:1459-1463); the ADHOC mesh velocity follows
+  // phase 1 (hydro2d.hpp:1510-1524): meshvel = (v, 0, 0) w + meshvel (1 - w), taken by the next step's fluxes
+  double vcx[HG_MAX_PHASES] = {0., 0., 0.};
+  for (int p = 0; p < c.num_phases; ++p) {
+    const double prev = s->stat_cx_set[p] ? s->stat_cx[p] : o.center[p][0];
+    vcx[p] = (o.center[p][0] - prev) / s->dt;
+    s->stat_cx[p] = o.center[p][0]; s->stat_cx_set[p] = true;
+  }
+  if (c.meshvel_auto) {
+    const double v0 = c.meshvel_auto == 1 ? o.velocity[1][0] : vcx[1], w = c.meshvel_weight;
+    for (int d = 0; d < 3; ++d) s->cfg.meshvel[d] = (d == 0 ? v0 : 0.) * w + s->cfg.meshvel[d] * (1. - w);
+  }
   if (c.meshvel_output) for (int d = 0; d < s->dim; ++d) s->meshpos[d] += c.meshvel[d] * s->dt;   // hydro2d.hpp:1526-1528
   if (st) {
     for (int p = 0; p < HG_MAX_PHASES; ++p) {
@@ -1474,6 +1487,7 @@ extern "C" void hg_config_defaults(hg_config* c) {   // examples/general.hydroco
   c->time_second_order = 1; c->rhie_chow_factor = 1.;
   c->initial_volume_fraction_smooth_times = 2; c->density_smooth_times = 2; c->viscosity_smooth_times = 2;
   c->heat_relaxation_factor = 1.; c->time_second_order_heat = 1; c->meshvel_output = 1;
+  c->meshvel_auto = 0; c->meshvel_weight = 0.5;
   c->world_size = 1;
 }
 
@@ -1550,6 +1564,9 @@ extern "C" int hg_create(const hg_config* cfg, hg_handle* out) {
   for (int ph = 0; ph < cfg->num_phases; ++ph)
     if (cfg->enable_settling[ph] && cfg->world_size > 1) return fail_create(nullptr, HG_ERR_INVALID, "multi-GPU slabs: phase slip is not decomposed");
   if (cfg->force_geometric_average) return fail_create(nullptr, HG_ERR_INVALID, "force_geometric_average 1 is not on the GPU path");
+  if (cfg->meshvel_auto < 0 || cfg->meshvel_auto > 2) return fail_create(nullptr, HG_ERR_INVALID, "Unknown meshvel_auto");
+  if (cfg->meshvel_auto && cfg->num_phases < 2) return fail_create(nullptr, HG_ERR_INVALID, "meshvel_auto follows phase 1: num_phases >= 2");
+  if (cfg->meshvel_auto && cfg->world_size > 1) return fail_create(nullptr, HG_ERR_INVALID, "multi-GPU slabs: meshvel_auto is not decomposed");
   for (int sd = 0; sd < 2 * cfg->dim; ++sd)
     if (cfg->condition_kind[sd] == HG_BC_OUTLET && cfg->world_size > 1) return fail_create(nullptr, HG_ERR_INVALID, "multi-GPU slabs: outlet conditions are not decomposed");
   for (int id : {cfg->linear_solver_velocity, cfg->linear_solver_pressure, cfg->linear_solver_heat})

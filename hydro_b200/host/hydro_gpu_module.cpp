@@ -108,8 +108,13 @@ class hydro_gpu : public TModule {
       if (flag(k)) throw std::runtime_error(std::string("hydro_gpu: ") + k + " 1 is not on the GPU path");
     if ((P_string.exist("chemistry") && P_string["chemistry"] != "steady") || (P_double.exist("chem_intensity") && P_double["chem_intensity"] != 0.))
       throw std::runtime_error("hydro_gpu: chemistry other than 'steady' with chem_intensity 0 is not on the GPU path");
-    for (const char* k : {"meshvel_auto", "imgu_init", "imgv_init", "img_init"})
+    for (const char* k : {"imgu_init", "imgv_init", "img_init"})
       if (P_string.exist(k)) throw std::runtime_error(std::string("hydro_gpu: ") + k + " is not on the GPU path");
+    if (std::string* ma = P_string("meshvel_auto")) {   // hydro2d.hpp:1510-1524
+      if (*ma == "vx") c.meshvel_auto = 1; else if (*ma == "vcx") c.meshvel_auto = 2;
+      else throw std::runtime_error("hydro_gpu: Unknown meshvel_auto=" + *ma);
+      c.meshvel_weight = P_double["meshvel_weight"];
+    }
     for (int i = 0; i < c.num_phases; ++i)
       if (flag("enable_settling_" + IntToStr(i))) { c.enable_settling[i] = 1; c.bubble_radius[i] = P_double["bubble_radius_" + IntToStr(i)]; }
     if (flag("velocity_is_carrier")) throw std::runtime_error("hydro_gpu: velocity_is_carrier 1 is not on the GPU path");

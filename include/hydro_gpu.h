@@ -148,7 +148,13 @@ typedef struct hg_config {
   int enable_settling[HG_MAX_PHASES];
   int velocity_is_carrier;
   double bubble_radius[HG_MAX_PHASES];
-  int reserved[6];
+  /* automatic mesh velocity (hydro<Mesh>::CalcStat, hydro2d.hpp:1510-1524; `set string meshvel_auto vx|vcx`): after the
+   * statistics of a step the mesh velocity is relaxed towards (v, 0, 0) with weight meshvel_weight, v = stat_vx_1 (1: mean
+   * x velocity of phase 1) or stat_vcx_1 (2: velocity of its centre); 0 = off.  Needs num_phases >= 2, one GPU. */
+  int meshvel_auto;
+  int reserved0;
+  double meshvel_weight;
+  int reserved[2];
 } hg_config;
 
 /* statistics of one hg_step, reference: P_int["s"], CalcStat (hydro2d.hpp:1432-1529) */

@@ -66,6 +66,7 @@ struct ho_state {
   int nres; double res_hist[4096];
   hg_step_stats stat;
   double meshpos[3];
+  double stat_cx[HG_MAX_PHASES]; int stat_cx_set[HG_MAX_PHASES];   /* P_double["stat_cx_<i>"] of the previous CalcStat */
   char err[256];
 };
 
@@ -981,6 +982,17 @@ int ho_calc_stat(ho_handle s, hg_step_stats* st) {                   /* hydro2d.
     st->pd_min[i] = pmin; st->pd_max[i] = pmax;
     for (int d = 0; d < 3; ++d) { st->center[i][d] = d < s->dim ? cen[d] / volume + s->meshpos[d] : 0.; st->velocity[i][d] = d < s->dim ? vel[d] / volume : 0.; }
   }
+  /* stat_vcx_<i> = (cx - previous cx) / dt, 0 at the first call (:1459-1463); ADHOC mesh velocity towards phase 1 (:1510-1524) */
+  double vcx[HG_MAX_PHASES];
+  for (int i = 0; i < s->cfg.num_phases; ++i) {
+    const double prev = s->stat_cx_set[i] ? s->stat_cx[i] : st->center[i][0];
+    vcx[i] = (st->center[i][0] - prev) / s->dt;
+    s->stat_cx[i] = st->center[i][0]; s->stat_cx_set[i] = 1;
+  }
+  if (s->cfg.meshvel_auto) {
+    const double v0 = s->cfg.meshvel_auto == 1 ? st->velocity[1][0] : vcx[1], w = s->cfg.meshvel_weight;
+    for (int d = 0; d < 3; ++d) s->cfg.meshvel[d] = (d == 0 ? v0 : 0.) * w + s->cfg.meshvel[d] * (1. - w);
+  }
   if (s->cfg.meshvel_output) for (int d = 0; d < s->dim; ++d) s->meshpos[d] += s->cfg.meshvel[d] * s->dt; /* :1526-1528 */
   return 0;
 }
@@ -1045,6 +1057,7 @@ void ho_config_defaults(hg_config* c) {          /* examples/general.hydroconf *
   c->time_second_order = 1; c->rhie_chow_factor = 1.;
   c->initial_volume_fraction_smooth_times = 2; c->density_smooth_times = 2; c->viscosity_smooth_times = 2;
   c->heat_relaxation_factor = 1.; c->time_second_order_heat = 1; c->meshvel_output = 1;
+  c->meshvel_auto = 0; c->meshvel_weight = 0.5;
   c->world_size = 1;
 }
 

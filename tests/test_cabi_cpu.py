@@ -103,6 +103,16 @@ def test_every_example_script_of_the_reference_parses():
     assert (c.dim, c.Nx, c.Ny, c.Nz) == (3, 167, 57, 62)
 
 
+def test_meshvel_auto_maps_to_the_struct():
+    """`set string meshvel_auto vx|vcx` (hydro2d.hpp:1510-1524; present = on, any other value is the reference's assert)."""
+    c = cases.broken_dam_2d(16, 8, meshvel_auto="vcx", meshvel_weight=0.25).to_struct()
+    assert (c.meshvel_auto, c.meshvel_weight) == (2, 0.25)
+    assert cases.broken_dam_2d(16, 8, meshvel_auto="vx").to_struct().meshvel_auto == 1
+    assert cases.broken_dam_2d(16, 8).to_struct().meshvel_auto == 0
+    with pytest.raises(ValueError, match="Unknown meshvel_auto"):
+        cases.broken_dam_2d(16, 8, meshvel_auto="phase0").to_struct()
+
+
 def test_missing_parameter_raises_like_reference():
     p = Params()
     del p["Nx"]
@@ -129,7 +139,7 @@ def test_product_does_not_import_oracle():
 
 
 @pytest.mark.parametrize("key,val", [("compressible_enable", 1), ("deforming_velocity", 1), ("radiation_enable", 1),
-                                     ("chemistry", "Nadirov"), ("chem_intensity", 0.5), ("meshvel_auto", "phase0"),
+                                     ("chemistry", "Nadirov"), ("chem_intensity", 0.5),
                                      ("imgu_init", "u.pgm"), ("velocity_is_carrier", 1), ("antidiffusion_factor", 0.3)])
 def test_options_outside_the_gpu_path_are_rejected(key, val):
     """Options that change the reference's results (hydro2d.hpp:326-368, 1030-1217, 1294, 1387, 1511-1524) must not be

@@ -99,12 +99,13 @@ def test_gpu_matches_oracle_and_reference_fixture(name):
     # device and host sin() in the initial velocity is amplified ~1e7 times in 3 steps; its exactness is
     # covered by test_gpu_bit_exact_from_identical_state instead
     loose = name == "rt3d_8_jacobi_dtauto"
-    gpu, cpu = run_both(p, nsteps, tol=1e-6 if loose else TOL, stat_tol=1e-6 if loose else 1e-11)
+    ill = cases.ILL_CONDITIONED.get(name)   # e.g. the mesh velocity from the differenced centre of a phase (see cases.py)
+    gpu, cpu = run_both(p, nsteps, tol=1e-6 if loose else (ill or TOL), stat_tol=1e-6 if loose else (ill or 1e-11))
     g = np.load(os.path.join(GOLD, "ref_%s.npz" % name))
     for fname, key in GOLD_KEYS.items():
         if key in g.files and has_field(cpu, fname):
             e = field_error(gpu, cpu, fname, ref=g[key])
-            assert e <= (1e-6 if loose else 1e-11), (fname, e)
+            assert e <= (1e-6 if loose else (ill or 1e-11)), (fname, e)
 
 
 @pytest.mark.parametrize("name", ["rt3d_16", "dam3d_32x10x10", "thermal2d_32x16", "cavity_16", "rt3d_8_jacobi_dtauto",
